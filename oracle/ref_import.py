@@ -1,0 +1,66 @@
+"""Import the UNMODIFIED reference modules from /root/reference (dev container only).
+
+TEST INFRASTRUCTURE ONLY.  ``/root/reference`` does not exist on the GPU box, so
+nothing that runs there (``-m gpu`` tests, ``smoke()``, ``bench.py``) may call
+this; it is used by ``oracle/make_golden.py`` and by the CPU tests that pin the
+oracle and the drop-in's state-dict contract against the real thing (skipped
+when the reference is absent).
+
+The reference's ``model.py`` / ``model_HoME.py`` import ``webdataset``, ``peft``
+and ``nltk`` at module top (model.py:7-18), none of which are installed here and
+none of which the hot-path classes use; empty stand-ins are pre-seeded in
+``sys.modules`` so the files import as they are.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+
+REFERENCE_DIR = os.environ.get("MMOE_REFERENCE_DIR", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_DIR, "model.py"))
+
+
+def _stub(name: str, **attrs):
+    if name in sys.modules:
+        return sys.modules[name]
+    try:
+        return importlib.import_module(name)
+    except Exception:
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+
+def _install_stubs():
+    _stub("webdataset")
+    _stub("peft", get_peft_model=lambda m, c: m, LoraConfig=lambda **k: None,
+          TaskType=types.SimpleNamespace(FEATURE_EXTRACTION="FEATURE_EXTRACTION"))
+    nltk = _stub("nltk")
+    tok = _stub("nltk.tokenize", sent_tokenize=lambda t: [s for s in t.split(". ") if s])
+    if not hasattr(nltk, "tokenize"):
+        nltk.tokenize = tok
+    _stub("matplotlib")
+    _stub("matplotlib.pyplot")
+
+
+def load_reference(which: str = "model"):
+    """Return the reference module object (``model`` or ``model_HoME``) under a
+    private name so it never shadows the drop-in ``model.py`` at the repo root."""
+    if not reference_available():
+        raise FileNotFoundError(f"reference not mounted at {REFERENCE_DIR}")
+    alias = f"_reference_{which}"
+    if alias in sys.modules:
+        return sys.modules[alias]
+    _install_stubs()
+    path = os.path.join(REFERENCE_DIR, which + ".py")
+    spec = importlib.util.spec_from_file_location(alias, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[alias] = mod
+    spec.loader.exec_module(mod)
+    return mod
