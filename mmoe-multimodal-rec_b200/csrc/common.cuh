@@ -1,0 +1,160 @@
+// Shared device/host helpers for the sm_100a MMoE kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/mmoe_b200.h"
+
+namespace mmoe {
+
+// ---------------------------------------------------------------- errors / launch count
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+cudaError_t last_launch_status(const char* what);
+
+#define MMOE_CHECK(cond, ...)            \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::mmoe::set_error(__VA_ARGS__);    \
+      return -1;                         \
+    }                                    \
+  } while (0)
+
+#define MMOE_CUDA(expr)                                                              \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      ::mmoe::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return -2;                                                                     \
+    }                                                                                \
+  } while (0)
+
+#define MMOE_LAUNCH_OK(what)                                                         \
+  do {                                                                               \
+    ::mmoe::count_launch();                                                          \
+    cudaError_t _e = cudaGetLastError();                                             \
+    if (_e != cudaSuccess) {                                                         \
+      ::mmoe::set_error("launch of %s failed: %s", what, cudaGetErrorString(_e));    \
+      return -3;                                                                     \
+    }                                                                                \
+  } while (0)
+
+#define MMOE_TRY(expr)        \
+  do {                        \
+    int _r = (expr);          \
+    if (_r != 0) return _r;   \
+  } while (0)
+
+// ---------------------------------------------------------------- dtype helpers
+template <typename T> struct DT;
+template <> struct DT<float> { static constexpr int id = MMOE_F32; };
+template <> struct DT<__nv_bfloat16> { static constexpr int id = MMOE_BF16; };
+template <> struct DT<__half> { static constexpr int id = MMOE_F16; };
+
+inline size_t dtype_size(int dtype) { return dtype == MMOE_F32 ? 4 : 2; }
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+
+// load/store element i of a buffer whose dtype is only known at run time
+__device__ __forceinline__ float load_as_f(const void* p, int64_t i, int dtype) {
+  if (dtype == MMOE_F32) return reinterpret_cast<const float*>(p)[i];
+  if (dtype == MMOE_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+  return __half2float(reinterpret_cast<const __half*>(p)[i]);
+}
+__device__ __forceinline__ void store_from_f(void* p, int64_t i, int dtype, float v) {
+  if (dtype == MMOE_F32) reinterpret_cast<float*>(p)[i] = v;
+  else if (dtype == MMOE_BF16) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
+}
+
+// ---------------------------------------------------------------- math
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// d/dx gelu(x) = Phi(x) + x * phi(x)
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------- dropout keep-mask
+// A counter-based hash of the flat element index, keyed per dropout site.  Any kernel can
+// regenerate the mask in backward from (key0, key1, index); no mask tensor is ever stored.
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
+  // keep iff (hash >> 8) >= p * 2^24
+  return (uint32_t)(p * 16777216.0f);
+}
+__host__ __device__ __forceinline__ bool drop_keep(uint32_t key0, uint32_t key1, uint64_t idx, uint32_t thresh) {
+  uint32_t x = (uint32_t)idx ^ ((uint32_t)(idx >> 32) * 0x632BE5ABu);
+  uint32_t h = mix32((x ^ key0) * 0x9E3779B1u);
+  h = mix32(h ^ key1);
+  return (h >> 8) >= thresh;
+}
+// per-site keys derived on the host from the call seed
+inline void site_keys(uint64_t seed, uint32_t site, uint32_t* k0, uint32_t* k1) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(site + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  *k0 = (uint32_t)z;
+  *k1 = (uint32_t)(z >> 32);
+}
+
+inline int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------- GEMM engine entry (gemm.cu)
+int gemm_grouped(const mmoe_gemm_problem* problems, int n_problems, int dtype, int engine, cudaStream_t stream);
+
+// convenience builders used by the orchestrators
+inline mmoe_epilogue epi_none() {
+  mmoe_epilogue e{};
+  e.alpha = 1.0f;
+  return e;
+}
+inline mmoe_gemm_problem gemm_problem(const void* a, int64_t lda, int a_major, const void* b, int64_t ldb, int b_major,
+                                      int M, int N, int K, const mmoe_epilogue& e, int k_splits = 1) {
+  mmoe_gemm_problem p{};
+  p.a = a; p.lda = lda; p.a_major = a_major;
+  p.b = b; p.ldb = ldb; p.b_major = b_major;
+  p.M = M; p.N = N; p.K = K; p.k_splits = k_splits; p.epi = e;
+  return p;
+}
+
+}  // namespace mmoe

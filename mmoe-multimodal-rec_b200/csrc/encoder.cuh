@@ -1,0 +1,231 @@
+// Pre-LN transformer encoder layer (RobustTransformerLayer, model.py:207-212; the stock
+// nn.TransformerEncoderLayer(norm_first=True) of EnhancedCrossFuse, model.py:460-465),
+// forward and backward, as a sequence of fused launches:
+//
+//   forward  : LN1 -> [QKV GEMM +bias] -> attention -> [out-proj GEMM +bias +dropout +residual]
+//              -> LN2 -> [FFN1 GEMM +bias +ReLU +dropout] -> [FFN2 GEMM +bias +dropout +residual]
+//   backward : cast/drop(+db2) -> {dgrad FFN2 (+ReLU/drop mask, +db1) | wgrad W2} -> {dgrad FFN1 | wgrad W1}
+//              -> LN2' (+residual, +dropout1 mask, +d b_out) -> {dgrad out-proj | wgrad Wo}
+//              -> attention' (+d b_in) -> {dgrad QKV | wgrad W_in} -> LN1' (+residual)
+//   "{a | b}" = one grouped GEMM launch.
+#pragma once
+#include "kernels.cuh"
+
+namespace mmoe {
+
+struct Arena {
+  char* base;
+  size_t off;
+  explicit Arena(void* b) : base(reinterpret_cast<char*>(b)), off(0) {}
+  void* take(size_t bytes) {
+    off = (off + 255) & ~(size_t)255;
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+// parameters / gradients of one encoder layer, in state_dict order (12 tensors)
+struct EncW {
+  const void* w_in; const float* b_in; const void* w_out; const float* b_out;
+  const void* w1; const float* b1; const void* w2; const float* b2;
+  const float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+};
+struct EncG {
+  float *w_in, *b_in, *w_out, *b_out, *w1, *b1, *w2, *b2, *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+};
+inline EncW enc_w(const void* const* p) {
+  EncW w;
+  w.w_in = p[0]; w.b_in = (const float*)p[1]; w.w_out = p[2]; w.b_out = (const float*)p[3];
+  w.w1 = p[4]; w.b1 = (const float*)p[5]; w.w2 = p[6]; w.b2 = (const float*)p[7];
+  w.ln1_w = (const float*)p[8]; w.ln1_b = (const float*)p[9]; w.ln2_w = (const float*)p[10]; w.ln2_b = (const float*)p[11];
+  return w;
+}
+inline EncG enc_g(void* const* p) {
+  EncG g;
+  g.w_in = (float*)p[0]; g.b_in = (float*)p[1]; g.w_out = (float*)p[2]; g.b_out = (float*)p[3];
+  g.w1 = (float*)p[4]; g.b1 = (float*)p[5]; g.w2 = (float*)p[6]; g.b2 = (float*)p[7];
+  g.ln1_w = (float*)p[8]; g.ln1_b = (float*)p[9]; g.ln2_w = (float*)p[10]; g.ln2_b = (float*)p[11];
+  return g;
+}
+
+// activations kept for backward
+struct EncSaved {
+  void* xn1; float* st1; void* qkv; void* ctx; float* x1; void* xn2; float* st2; void* h; float* x2;
+};
+inline EncSaved enc_layout(Arena& A, int64_t M, int d, int ff, size_t es) {
+  EncSaved s;
+  s.xn1 = A.take(M * d * es);
+  s.st1 = (float*)A.take(M * 2 * sizeof(float));
+  s.qkv = A.take(M * 3 * d * es);
+  s.ctx = A.take(M * d * es);
+  s.x1 = (float*)A.take(M * d * sizeof(float));
+  s.xn2 = A.take(M * d * es);
+  s.st2 = (float*)A.take(M * 2 * sizeof(float));
+  s.h = A.take(M * ff * es);
+  s.x2 = (float*)A.take(M * d * sizeof(float));
+  return s;
+}
+// scratch of the backward pass
+struct EncScratch {
+  void* g; void* dh; void* dxn; float* dx1; void* dqkv; void* dctx;
+};
+inline EncScratch enc_scratch_layout(Arena& A, int64_t M, int d, int ff, size_t es) {
+  EncScratch s;
+  s.g = A.take(M * d * es);
+  s.dh = A.take(M * ff * es);
+  s.dxn = A.take(M * d * es);
+  s.dx1 = (float*)A.take(M * d * sizeof(float));
+  s.dqkv = A.take(M * 3 * d * es);
+  s.dctx = A.take(M * d * es);
+  return s;
+}
+
+struct EncCtx {
+  int dtype; int64_t M; int Bseq, S, d, ff, H;
+  const uint8_t* mask;        // [Bseq,S] or null
+  float drop_p;               // 0 in eval
+  uint64_t seed; uint32_t site0;   // 4 dropout sites: site0 + {0 probs, 1 dropout1, 2 ffn, 3 dropout2}
+  cudaStream_t stream;
+};
+
+inline int wgrad_splits(int M, int N, int K) {
+  const int tiles = ((M + 127) / 128) * ((N + 255) / 256);
+  const int kb = (K + 63) / 64;
+  int ks = (2 * sm_count() + tiles - 1) / tiles;
+  const int max_ks = kb / 4 > 1 ? kb / 4 : 1;
+  if (ks > max_ks) ks = max_ks;
+  return ks < 1 ? 1 : ks;
+}
+
+// y = epilogue(x W^T + b): nn.Linear forward
+inline mmoe_gemm_problem linear_fwd(const void* x, int64_t ldx, const void* w, int M, int N, int K, const mmoe_epilogue& e) {
+  return gemm_problem(x, ldx, 0, w, K, 0, M, N, K, e);
+}
+// dx[M,K] = epilogue(dy[M,N] W[N,K])
+inline mmoe_gemm_problem linear_dgrad(const void* dy, int64_t lddy, const void* w, int M, int N, int K, const mmoe_epilogue& e) {
+  return gemm_problem(dy, lddy, 0, w, K, 1, M, K, N, e);
+}
+// dW[N,K] += dy[M,N]^T x[M,K]   (fp32 atomic accumulation, split over M)
+inline mmoe_gemm_problem linear_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx, float* dw, int M, int N, int K) {
+  mmoe_epilogue e = epi_none();
+  e.out = dw; e.out_dtype = MMOE_F32; e.ldo = K; e.accumulate = 1;
+  return gemm_problem(dy, lddy, 1, x, ldx, 1, N, K, M, e, wgrad_splits(N, K, M));
+}
+
+inline int enc_fwd(const EncCtx& c, const EncW& w, const float* x_in, const EncSaved& s) {
+  const int d = c.d, ff = c.ff; const int M = (int)c.M;
+  const size_t es = dtype_size(c.dtype);
+  uint32_t k0, k1;
+  MMOE_TRY(layernorm_fwd(x_in, MMOE_F32, w.ln1_w, w.ln1_b, s.xn1, nullptr, s.st1, M, d, c.dtype, c.stream));
+  {
+    mmoe_epilogue e = epi_none();
+    e.out = s.qkv; e.out_dtype = c.dtype; e.ldo = 3 * d; e.bias = w.b_in;
+    mmoe_gemm_problem p = linear_fwd(s.xn1, d, w.w_in, M, 3 * d, d, e);
+    MMOE_TRY(gemm_grouped(&p, 1, c.dtype, 0, c.stream));
+  }
+  {
+    AttnArgs a{};
+    a.q = s.qkv; a.k = (const char*)s.qkv + (size_t)d * es; a.v = (const char*)s.qkv + (size_t)2 * d * es;
+    a.ldq = a.ldk = a.ldv = 3 * d; a.mask = c.mask; a.ctx = s.ctx; a.ldc = d;
+    a.B = c.Bseq; a.Sq = c.S; a.Sk = c.S; a.H = c.H; a.hd = d / c.H;
+    site_keys(c.seed, c.site0 + 0, &k0, &k1);
+    a.drop_p = c.drop_p; a.k0 = k0; a.k1 = k1; a.dtype = c.dtype;
+    MMOE_TRY(attention_fwd(a, c.stream));
+  }
+  {
+    mmoe_epilogue e = epi_none();
+    e.out = s.x1; e.out_dtype = MMOE_F32; e.ldo = d; e.bias = w.b_out; e.residual = x_in; e.ld_res = d;
+    site_keys(c.seed, c.site0 + 1, &k0, &k1);
+    e.drop_p = c.drop_p; e.drop_key0 = k0; e.drop_key1 = k1;
+    mmoe_gemm_problem p = linear_fwd(s.ctx, d, w.w_out, M, d, d, e);
+    MMOE_TRY(gemm_grouped(&p, 1, c.dtype, 0, c.stream));
+  }
+  MMOE_TRY(layernorm_fwd(s.x1, MMOE_F32, w.ln2_w, w.ln2_b, s.xn2, nullptr, s.st2, M, d, c.dtype, c.stream));
+  {
+    mmoe_epilogue e = epi_none();
+    e.out = s.h; e.out_dtype = c.dtype; e.ldo = ff; e.bias = w.b1; e.act = 1;
+    site_keys(c.seed, c.site0 + 2, &k0, &k1);
+    e.drop_p = c.drop_p; e.drop_key0 = k0; e.drop_key1 = k1;
+    mmoe_gemm_problem p = linear_fwd(s.xn2, d, w.w1, M, ff, d, e);
+    MMOE_TRY(gemm_grouped(&p, 1, c.dtype, 0, c.stream));
+  }
+  {
+    mmoe_epilogue e = epi_none();
+    e.out = s.x2; e.out_dtype = MMOE_F32; e.ldo = d; e.bias = w.b2; e.residual = s.x1; e.ld_res = d;
+    site_keys(c.seed, c.site0 + 3, &k0, &k1);
+    e.drop_p = c.drop_p; e.drop_key0 = k0; e.drop_key1 = k1;
+    mmoe_gemm_problem p = linear_fwd(s.h, ff, w.w2, M, d, ff, e);
+    MMOE_TRY(gemm_grouped(&p, 1, c.dtype, 0, c.stream));
+  }
+  return 0;
+}
+
+// dy: gradient w.r.t. the layer output (fp32 [M,d]); dx: gradient w.r.t. the layer input (fp32, may alias dy)
+inline int enc_bwd(const EncCtx& c, const EncW& w, const EncG& g, const float* x_in, const EncSaved& s, const EncScratch& t,
+                   const float* dy, float* dx) {
+  const int d = c.d, ff = c.ff; const int M = (int)c.M;
+  const size_t es = dtype_size(c.dtype);
+  uint32_t k0, k1;
+  // FFN2: x2 = x1 + drop2(h W2^T + b2)
+  site_keys(c.seed, c.site0 + 3, &k0, &k1);
+  MMOE_TRY(cast_drop_colsum(dy, t.g, g.b2, M, d, c.drop_p, k0, k1, c.dtype, c.stream));
+  {
+    mmoe_epilogue e = epi_none();
+    e.out = t.dh; e.out_dtype = c.dtype; e.ldo = ff; e.bwd_mode = 1; e.aux = s.h; e.ld_aux = ff; e.colsum = g.b1;
+    e.drop_p = c.drop_p;   // only the 1/(1-p) scale is used in bwd_mode 1 (the mask is h != 0)
+    mmoe_gemm_problem p[2] = {linear_dgrad(t.g, d, w.w2, M, d, ff, e), linear_wgrad(t.g, d, s.h, ff, g.w2, M, d, ff)};
+    MMOE_TRY(gemm_grouped(p, 2, c.dtype, 0, c.stream));
+  }
+  // FFN1: h = drop(relu(xn2 W1^T + b1))
+  {
+    mmoe_epilogue e = epi_none();
+    e.out = t.dxn; e.out_dtype = c.dtype; e.ldo = d;
+    mmoe_gemm_problem p[2] = {linear_dgrad(t.dh, ff, w.w1, M, ff, d, e), linear_wgrad(t.dh, ff, s.xn2, d, g.w1, M, ff, d)};
+    MMOE_TRY(gemm_grouped(p, 2, c.dtype, 0, c.stream));
+  }
+  // LN2 and the residual: dx1 = dy + LN2'(dxn);  g = drop1-mask(dx1) for the out-proj backward (+ d b_out)
+  {
+    LnBwdArgs a{};
+    a.dy = t.dxn; a.dy_dtype = c.dtype; a.x = s.x1; a.x_dtype = MMOE_F32; a.stats = s.st2; a.gamma = w.ln2_w;
+    a.dres = dy; a.dx = t.dx1; a.dgamma = g.ln2_w; a.dbeta = g.ln2_b; a.g_out = t.g; a.g_colsum = g.b_out;
+    site_keys(c.seed, c.site0 + 1, &k0, &k1);
+    a.drop_p = c.drop_p; a.k0 = k0; a.k1 = k1; a.rows = M; a.d = d; a.dtype = c.dtype;
+    MMOE_TRY(layernorm_bwd(a, c.stream));
+  }
+  // out-proj: x1 = x_in + drop1(ctx Wo^T + bo)
+  {
+    mmoe_epilogue e = epi_none();
+    e.out = t.dctx; e.out_dtype = c.dtype; e.ldo = d;
+    mmoe_gemm_problem p[2] = {linear_dgrad(t.g, d, w.w_out, M, d, d, e), linear_wgrad(t.g, d, s.ctx, d, g.w_out, M, d, d)};
+    MMOE_TRY(gemm_grouped(p, 2, c.dtype, 0, c.stream));
+  }
+  {
+    AttnArgs a{};
+    a.q = s.qkv; a.k = (const char*)s.qkv + (size_t)d * es; a.v = (const char*)s.qkv + (size_t)2 * d * es;
+    a.ldq = a.ldk = a.ldv = 3 * d; a.mask = c.mask; a.ctx = t.dctx; a.ldc = d;
+    a.dq = t.dqkv; a.dk = (char*)t.dqkv + (size_t)d * es; a.dv = (char*)t.dqkv + (size_t)2 * d * es;
+    a.bgq = g.b_in; a.bgk = g.b_in + d; a.bgv = g.b_in + 2 * d;
+    a.B = c.Bseq; a.Sq = c.S; a.Sk = c.S; a.H = c.H; a.hd = d / c.H;
+    site_keys(c.seed, c.site0 + 0, &k0, &k1);
+    a.drop_p = c.drop_p; a.k0 = k0; a.k1 = k1; a.dtype = c.dtype;
+    MMOE_TRY(attention_bwd(a, c.stream));
+  }
+  {
+    mmoe_epilogue e = epi_none();
+    e.out = t.dxn; e.out_dtype = c.dtype; e.ldo = d;
+    mmoe_gemm_problem p[2] = {linear_dgrad(t.dqkv, 3 * d, w.w_in, M, 3 * d, d, e),
+                              linear_wgrad(t.dqkv, 3 * d, s.xn1, d, g.w_in, M, 3 * d, d)};
+    MMOE_TRY(gemm_grouped(p, 2, c.dtype, 0, c.stream));
+  }
+  {
+    LnBwdArgs a{};
+    a.dy = t.dxn; a.dy_dtype = c.dtype; a.x = x_in; a.x_dtype = MMOE_F32; a.stats = s.st1; a.gamma = w.ln1_w;
+    a.dres = t.dx1; a.dx = dx; a.dgamma = g.ln1_w; a.dbeta = g.ln1_b;
+    a.rows = M; a.d = d; a.dtype = c.dtype;
+    MMOE_TRY(layernorm_bwd(a, c.stream));
+  }
+  return 0;
+}
+
+}  // namespace mmoe

@@ -1,0 +1,589 @@
+// GEMM engine of the MMoE path: D[M,N] = epilogue(sum_k A(m,k) B(n,k)).
+//
+//  * gemm_tc_kernel   — 16-bit operands on the 5th-gen tensor cores: tcgen05.mma
+//                       (cta_group::1, 128x256x16, kind::f16) issued by one thread,
+//                       operands staged by TMA (128B swizzle) through a 4-deep mbarrier ring,
+//                       fp32 accumulators double-buffered in TMEM (2 x 256 columns) so the
+//                       epilogue of tile i overlaps the MMAs of tile i+1.  Persistent grid,
+//                       up to 8 problems per launch (grouped), optional split-K.
+//  * gemm_simt_kernel — fp32 (exact) path and cross-check: 128x128x16 FFMA tiles.
+//
+// Both share one fused epilogue (bias, activation, backward multipliers, dropout, residual,
+// column sums for bias gradients, split-K accumulation); see mmoe_epilogue in the header.
+// K-major and MN-major operands are both consumed directly (UMMA descriptors with the
+// transpose bits), so forward, dgrad and wgrad need no transposed copies.
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace mmoe {
+
+constexpr int kMaxGroups = 8;
+
+// ------------------------------------------------------------------------------------------
+// shared epilogue
+// ------------------------------------------------------------------------------------------
+struct EpiDev {
+  mmoe_epilogue e;
+  int op_dtype;        // dtype of preact / aux / non-fp32 out
+  uint32_t thresh;     // dropout threshold
+  float drop_scale;    // 1/(1-p)
+};
+
+__device__ __forceinline__ float epi_value(const EpiDev& d, int N, int m, int n, float acc, bool first_split) {
+  const mmoe_epilogue& e = d.e;
+  float v = e.alpha * acc;
+  if (e.bias != nullptr && first_split) v += __ldg(e.bias + n);
+  if (e.preact != nullptr) store_from_f(e.preact, (int64_t)m * e.ldo + n, d.op_dtype, v);
+  if (e.act == 1) v = fmaxf(v, 0.0f);
+  else if (e.act == 2) v = gelu_f(v);
+  else if (e.act == 3) v = sigmoid_f(v);
+  bool dropped_by_aux = false;
+  if (e.bwd_mode != 0) {
+    const float a = load_as_f(e.aux, (int64_t)m * e.ld_aux + n, d.op_dtype);
+    if (e.bwd_mode == 1) {
+      v = (a != 0.0f) ? v * d.drop_scale : 0.0f;
+      dropped_by_aux = true;
+    } else if (e.bwd_mode == 2) {
+      v *= gelu_grad_f(a);
+    } else {
+      const float s = sigmoid_f(a);
+      v *= s * (1.0f - s);
+    }
+  }
+  if (e.drop_p > 0.0f && !dropped_by_aux) {
+    v = drop_keep(e.drop_key0, e.drop_key1, (uint64_t)m * (uint64_t)N + (uint64_t)n, d.thresh) ? v * d.drop_scale : 0.0f;
+  }
+  if (e.residual != nullptr && first_split) v += __ldg(e.residual + (int64_t)m * e.ld_res + n);
+  return v;
+}
+
+__device__ __forceinline__ void epi_store(const EpiDev& d, int m, int n, float v) {
+  const mmoe_epilogue& e = d.e;
+  if (e.out == nullptr) return;
+  const int64_t off = (int64_t)m * e.ldo + n;
+  if (e.accumulate) atomicAdd(reinterpret_cast<float*>(e.out) + off, v);
+  else store_from_f(e.out, off, e.out_dtype, v);
+}
+
+// ------------------------------------------------------------------------------------------
+// grouped problem table (kernel parameter)
+// ------------------------------------------------------------------------------------------
+struct alignas(64) TcGroup {
+  CUtensorMap tma_a;
+  CUtensorMap tma_b;
+  EpiDev epi;
+  int M, N, K;
+  int tiles_m, tiles_n, k_splits, kb_total, kb_per_split;
+  int tile_begin;
+  int a_major, b_major;
+};
+struct alignas(64) TcParams {
+  TcGroup g[kMaxGroups];
+  int n_groups;
+  int total_tiles;
+  int fmt;  // 0 f16, 1 bf16
+};
+
+struct SimtGroup {
+  const void* a; const void* b;
+  int64_t sam, sak, sbn, sbk;   // element strides of A(m,k), B(n,k)
+  EpiDev epi;
+  int M, N, K;
+  int tiles_m, tiles_n, k_splits, k_per_split;
+  int tile_begin;
+};
+struct SimtParams {
+  SimtGroup g[kMaxGroups];
+  int n_groups;
+  int total_tiles;
+};
+
+// ------------------------------------------------------------------------------------------
+// SIMT kernel (fp32 path + cross-check).  128x128x16 tile, 256 threads, 8x8 per thread.
+// ------------------------------------------------------------------------------------------
+constexpr int SBM = 128, SBN = 128, SBK = 16, SPAD = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const __grid_constant__ SimtParams p) {
+  __shared__ float As[SBK][SBM + SPAD];
+  __shared__ float Bs[SBK][SBN + SPAD];
+  const int tile = blockIdx.x;
+  int gi = 0;
+  for (int i = 1; i < p.n_groups; ++i) if (tile >= p.g[i].tile_begin) gi = i;
+  const SimtGroup& g = p.g[gi];
+  int local = tile - g.tile_begin;
+  const int split = local % g.k_splits; local /= g.k_splits;
+  const int n_blk = local % g.tiles_n;
+  const int m_blk = local / g.tiles_n;
+  const int m0 = m_blk * SBM, n0 = n_blk * SBN;
+  const int k_begin = split * g.k_per_split;
+  const int k_end = min(g.K, k_begin + g.k_per_split);
+  const T* __restrict__ A = reinterpret_cast<const T*>(g.a);
+  const T* __restrict__ B = reinterpret_cast<const T*>(g.b);
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+
+  const bool a_kmajor = (g.sak == 1), b_kmajor = (g.sbk == 1);
+  for (int k0 = k_begin; k0 < k_end; k0 += SBK) {
+    // 128x16 elements per operand, 8 per thread; mapping follows the contiguous dimension
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int mm, kk;
+      if (a_kmajor) { kk = tid & 15; mm = (tid >> 4) + 16 * i; }
+      else          { mm = tid & 127; kk = (tid >> 7) + 2 * i; }
+      const int m = m0 + mm, k = k0 + kk;
+      float v = 0.0f;
+      if (m < g.M && k < k_end) v = to_f<T>(A[(int64_t)m * g.sam + (int64_t)k * g.sak]);
+      As[kk][mm] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int nn, kk;
+      if (b_kmajor) { kk = tid & 15; nn = (tid >> 4) + 16 * i; }
+      else          { nn = tid & 127; kk = (tid >> 7) + 2 * i; }
+      const int n = n0 + nn, k = k0 + kk;
+      float v = 0.0f;
+      if (n < g.N && k < k_end) v = to_f<T>(B[(int64_t)n * g.sbn + (int64_t)k * g.sbk]);
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SBK; ++kk) {
+      float a[8], b[8];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const bool first = (split == 0);
+  float csum[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) csum[j] = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (n >= g.N) continue;
+      const float v = epi_value(g.epi, g.N, m, n, acc[i][j], first);
+      csum[j] += v;
+      epi_store(g.epi, m, n, v);
+    }
+  }
+  if (g.epi.e.colsum != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (n < g.N) atomicAdd(g.epi.e.colsum + n, csum[j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// tcgen05 kernel
+// ------------------------------------------------------------------------------------------
+constexpr int TBM = 128, TBN = 256, TBK = 64, TSTAGES = 4;
+constexpr int TA_BYTES = TBM * TBK * 2;   // 16 KB
+constexpr int TB_BYTES = TBN * TBK * 2;   // 32 KB
+constexpr int TSTAGE_BYTES = TA_BYTES + TB_BYTES;
+constexpr int TEPI_PITCH = 33;
+constexpr int TEPI_BYTES = 4 * 32 * TEPI_PITCH * 4;
+constexpr int TC_SMEM_BYTES = 1024 /*align slack*/ + TSTAGES * TSTAGE_BYTES + TEPI_BYTES + 256 /*barriers*/;
+constexpr int TC_THREADS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  const long long t0 = clock64();
+  do {
+    // a pipeline bug must surface as a launch error, never as a hung GPU: give up after ~2 s
+    if (clock64() - t0 > 4000000000ll) __trap();
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// UMMA shared-memory matrix descriptor (SM100): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 |
+// layout SWIZZLE_128B (2) <<61.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TileInfo {
+  int gi, m_blk, n_blk, split, kb0, kb1;
+};
+__device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int tile) {
+  TileInfo t;
+  t.gi = 0;
+  for (int i = 1; i < p.n_groups; ++i) if (tile >= p.g[i].tile_begin) t.gi = i;
+  const TcGroup& g = p.g[t.gi];
+  int local = tile - g.tile_begin;
+  t.split = local % g.k_splits; local /= g.k_splits;
+  t.n_blk = local % g.tiles_n;
+  t.m_blk = local / g.tiles_n;
+  t.kb0 = t.split * g.kb_per_split;
+  t.kb1 = min(g.kb_total, t.kb0 + g.kb_per_split);
+  return t;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t smem_a0 = smem_base;
+  const uint32_t smem_b0 = smem_base + TSTAGES * TA_BYTES;
+  float* epi_stage = reinterpret_cast<float*>(smem_gen + TSTAGES * TSTAGE_BYTES);
+  const uint32_t bar_base = smem_base + TSTAGES * TSTAGE_BYTES + TEPI_BYTES;
+  // barrier layout: full[4], empty[4], tmem_full[2], tmem_empty[2], then the TMEM base slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (TSTAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * TSTAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * TSTAGES + 2 + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + TSTAGES * TSTAGE_BYTES + TEPI_BYTES + 8 * (2 * TSTAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < TSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileInfo t = decode_tile(p, tile);
+        const TcGroup& g = p.g[t.gi];
+        const int m0 = t.m_blk * TBM, n0 = t.n_blk * TBN;
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), TSTAGE_BYTES);
+          const uint32_t sa = smem_a0 + stage * TA_BYTES, sb = smem_b0 + stage * TB_BYTES;
+          const int k0 = kb * TBK;
+          if (g.a_major == 0) {
+            tma_load_2d(sa, &g.tma_a, full_bar(stage), k0, m0);                 // box {64 k, 128 m}
+          } else {
+#pragma unroll
+            for (int j = 0; j < TBM / 64; ++j)                                  // boxes {64 m, 64 k}
+              tma_load_2d(sa + j * (TBK * 128), &g.tma_a, full_bar(stage), m0 + j * 64, k0);
+          }
+          if (g.b_major == 0) {
+            tma_load_2d(sb, &g.tma_b, full_bar(stage), k0, n0);                 // box {64 k, 256 n}
+          } else {
+#pragma unroll
+            for (int j = 0; j < TBN / 64; ++j)                                  // boxes {64 n, 64 k}
+              tma_load_2d(sb + j * (TBK * 128), &g.tma_b, full_bar(stage), n0 + j * 64, k0);
+          }
+          if (++stage == TSTAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileInfo t = decode_tile(p, tile);
+        const TcGroup& g = p.g[t.gi];
+        // instruction descriptor: D fp32, A/B f16|bf16, majors, N>>3, M>>4
+        const uint32_t idesc = (1u << 4) | ((uint32_t)p.fmt << 7) | ((uint32_t)p.fmt << 10) |
+                               ((uint32_t)g.a_major << 15) | ((uint32_t)g.b_major << 16) |
+                               ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * TBN);
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_a0 + stage * TA_BYTES, sb = smem_b0 + stage * TB_BYTES;
+#pragma unroll
+          for (int k = 0; k < TBK / 16; ++k) {
+            // K-major: 8-row groups 1024 B apart (SBO), 32 B per UMMA_K step inside the 128 B swizzle row.
+            // MN-major: 64-element column blocks TBK*128 B apart (LBO), 8-k groups 1024 B apart (SBO),
+            //           16 k-rows (2048 B) per UMMA_K step.
+            const uint64_t adesc = g.a_major == 0 ? umma_desc(sa + k * 32, 16, 1024) : umma_desc(sa + k * 2048, TBK * 128, 1024);
+            const uint64_t bdesc = g.b_major == 0 ? umma_desc(sb + k * 32, 16, 1024) : umma_desc(sb + k * 2048, TBK * 128, 1024);
+            tc_mma_f16(tmem_d, adesc, bdesc, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));      // frees the smem slot once these MMAs have read it
+          if (++stage == TSTAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(as));           // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps (TMEM -> regs -> smem transpose -> global) =====================
+    const int quad = warp & 3;              // TMEM lane quadrant this warp may read
+    float* st = epi_stage + quad * 32 * TEPI_PITCH;
+    int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileInfo t = decode_tile(p, tile);
+      const TcGroup& g = p.g[t.gi];
+      const int m0 = t.m_blk * TBM + quad * 32, n0 = t.n_blk * TBN;
+      const bool first = (t.split == 0);
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const int rows = min(32, g.M - m0);   // may be <= 0 for a ragged last tile
+#pragma unroll 1
+      for (int c = 0; c < TBN / 32; ++c) {
+        const int nb = n0 + c * 32;
+        if (nb >= g.N) break;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * TBN + c * 32), v);
+        if (rows > 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) st[lane * TEPI_PITCH + j] = __uint_as_float(v[j]);
+          __syncwarp();
+          const int n = nb + lane;
+          if (n < g.N) {
+            float csum = 0.0f;
+            for (int r = 0; r < rows; ++r) {
+              const float val = epi_value(g.epi, g.N, m0 + r, n, st[r * TEPI_PITCH + lane], first);
+              csum += val;
+              epi_store(g.epi, m0 + r, n, val);
+            }
+            if (g.epi.e.colsum != nullptr) atomicAdd(g.epi.e.colsum + n, csum);
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D bf16/f16 tensor [rows][cols] (cols contiguous, row stride ld elements); box {64 cols, box_rows}, 128B swizzle
+static int make_tmap(CUtensorMap* map, const void* ptr, int dtype, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  MMOE_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  MMOE_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "GEMM operand pointer must be 16-byte aligned");
+  MMOE_CHECK((ld * 2) % 16 == 0, "GEMM operand leading dimension must be a multiple of 8 elements (got %lld)", (long long)ld);
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(map, dtype == MMOE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                  const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MMOE_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r,
+             (long long)rows, (long long)cols, (long long)ld);
+  return 0;
+}
+
+static int fill_epi(EpiDev* d, const mmoe_gemm_problem& pr, int dtype) {
+  d->e = pr.epi;
+  d->op_dtype = dtype;
+  d->thresh = drop_threshold(pr.epi.drop_p);
+  d->drop_scale = pr.epi.drop_p > 0.0f ? 1.0f / (1.0f - pr.epi.drop_p) : 1.0f;
+  if (d->e.out != nullptr && d->e.out_dtype != MMOE_F32) d->e.out_dtype = dtype;
+  MMOE_CHECK(!(pr.epi.accumulate && pr.epi.out_dtype != MMOE_F32), "accumulate needs an fp32 output");
+  if (pr.k_splits > 1) {
+    MMOE_CHECK(pr.epi.accumulate, "k_splits > 1 needs epi.accumulate");
+    MMOE_CHECK(pr.epi.act == 0 && pr.epi.preact == nullptr && pr.epi.bwd_mode == 0,
+               "split-K only supports linear epilogues");
+  }
+  return 0;
+}
+
+static int launch_tc(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream_t stream) {
+  TcParams P{};
+  P.n_groups = n;
+  P.fmt = dtype == MMOE_BF16 ? 1 : 0;
+  int tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    TcGroup& g = P.g[i];
+    const mmoe_gemm_problem& q = pr[i];
+    g.M = q.M; g.N = q.N; g.K = q.K;
+    g.a_major = q.a_major; g.b_major = q.b_major;
+    if (q.a_major == 0) MMOE_TRY(make_tmap(&g.tma_a, q.a, dtype, q.M, q.K, q.lda, TBM));
+    else                MMOE_TRY(make_tmap(&g.tma_a, q.a, dtype, q.K, q.M, q.lda, TBK));
+    if (q.b_major == 0) MMOE_TRY(make_tmap(&g.tma_b, q.b, dtype, q.N, q.K, q.ldb, TBN));
+    else                MMOE_TRY(make_tmap(&g.tma_b, q.b, dtype, q.K, q.N, q.ldb, TBK));
+    MMOE_TRY(fill_epi(&g.epi, q, dtype));
+    g.tiles_m = (q.M + TBM - 1) / TBM;
+    g.tiles_n = (q.N + TBN - 1) / TBN;
+    g.kb_total = (q.K + TBK - 1) / TBK;
+    int ks = q.k_splits < 1 ? 1 : q.k_splits;
+    if (ks > g.kb_total) ks = g.kb_total;
+    g.kb_per_split = (g.kb_total + ks - 1) / ks;
+    g.k_splits = (g.kb_total + g.kb_per_split - 1) / g.kb_per_split;
+    g.tile_begin = tiles;
+    tiles += g.tiles_m * g.tiles_n * g.k_splits;
+  }
+  P.total_tiles = tiles;
+  if (tiles == 0) return 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MMOE_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(P);
+  MMOE_LAUNCH_OK("gemm_tc_kernel");
+  return 0;
+}
+
+template <typename T>
+static int launch_simt(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream_t stream) {
+  SimtParams P{};
+  P.n_groups = n;
+  int tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    SimtGroup& g = P.g[i];
+    const mmoe_gemm_problem& q = pr[i];
+    g.a = q.a; g.b = q.b;
+    g.M = q.M; g.N = q.N; g.K = q.K;
+    if (q.a_major == 0) { g.sam = q.lda; g.sak = 1; } else { g.sam = 1; g.sak = q.lda; }
+    if (q.b_major == 0) { g.sbn = q.ldb; g.sbk = 1; } else { g.sbn = 1; g.sbk = q.ldb; }
+    MMOE_TRY(fill_epi(&g.epi, q, dtype));
+    g.tiles_m = (q.M + SBM - 1) / SBM;
+    g.tiles_n = (q.N + SBN - 1) / SBN;
+    int ks = q.k_splits < 1 ? 1 : q.k_splits;
+    int kper = ((q.K + ks - 1) / ks + SBK - 1) / SBK * SBK;
+    if (kper < SBK) kper = SBK;
+    g.k_per_split = kper;
+    g.k_splits = (q.K + kper - 1) / kper;
+    if (g.k_splits < 1) g.k_splits = 1;
+    g.tile_begin = tiles;
+    tiles += g.tiles_m * g.tiles_n * g.k_splits;
+  }
+  P.total_tiles = tiles;
+  if (tiles == 0) return 0;
+  gemm_simt_kernel<T><<<tiles, 256, 0, stream>>>(P);
+  MMOE_LAUNCH_OK("gemm_simt_kernel");
+  return 0;
+}
+
+int gemm_grouped(const mmoe_gemm_problem* problems, int n_problems, int dtype, int engine, cudaStream_t stream) {
+  MMOE_CHECK(n_problems >= 1 && n_problems <= kMaxGroups, "n_problems must be in [1,%d]", kMaxGroups);
+  for (int i = 0; i < n_problems; ++i) {
+    const mmoe_gemm_problem& q = problems[i];
+    MMOE_CHECK(q.M >= 0 && q.N >= 1 && q.K >= 1, "bad GEMM dims %d %d %d", q.M, q.N, q.K);
+    MMOE_CHECK(q.a != nullptr && q.b != nullptr, "null GEMM operand");
+  }
+  if (dtype == MMOE_F32) return launch_simt<float>(problems, n_problems, dtype, stream);
+  static const bool force_simt = getenv("MMOE_DEBUG_FORCE_SIMT") != nullptr;   // test-only cross-check switch
+  if (engine == 1 || force_simt) {
+    if (dtype == MMOE_BF16) return launch_simt<__nv_bfloat16>(problems, n_problems, dtype, stream);
+    return launch_simt<__half>(problems, n_problems, dtype, stream);
+  }
+  return launch_tc(problems, n_problems, dtype, stream);
+}
+
+}  // namespace mmoe
+
+extern "C" int mmoe_gemm_grouped(const mmoe_gemm_problem* problems, int n_problems, int dtype, int engine, void* stream) {
+  return mmoe::gemm_grouped(problems, n_problems, dtype, engine, reinterpret_cast<cudaStream_t>(stream));
+}

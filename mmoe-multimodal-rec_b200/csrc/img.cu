@@ -1,0 +1,231 @@
+// Image-expert wrappers.
+//  * ItemImageExpert after the backbone (model.py:377-385): token mean / CLS -> LayerNorm -> dropout,
+//    one HBM-bound kernel (reads [n_tok, d] per sample once, coalesced).
+//  * ImageExpertWithProjection.projection_head (model_HoME.py:383-387): Linear-GELU-Linear on the GEMM engine.
+#include "encoder.cuh"
+
+namespace mmoe {
+
+template <typename TT>
+__global__ void __launch_bounds__(256) img_pool_fwd_kernel(const TT* __restrict__ tokens, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float* __restrict__ out,
+                                                           float* __restrict__ stats, float* __restrict__ pooled, int n_tok, int d,
+                                                           int pool_cls, uint32_t thresh, float scale, uint32_t k0, uint32_t k1) {
+  __shared__ float red[8];
+  __shared__ float bc[2];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const TT* tk = tokens + (int64_t)b * n_tok * d;
+  float v[4];   // d <= 1024
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = threadIdx.x + 256 * i;
+    v[i] = 0.f;
+    if (c < d) {
+      if (pool_cls) v[i] = to_f<TT>(tk[c]);
+      else {
+        float acc = 0.f;
+        for (int t = 0; t < n_tok; ++t) acc += to_f<TT>(tk[(int64_t)t * d + c]);
+        v[i] = acc / (float)n_tok;
+      }
+      pooled[(int64_t)b * d + c] = v[i];
+      sum += v[i];
+    }
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < 8; ++w) t += red[w]; bc[0] = t / (float)d; }
+  __syncthreads();
+  const float mean = bc[0];
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const int c = threadIdx.x + 256 * i; if (c < d) sq += (v[i] - mean) * (v[i] - mean); }
+  sq = warp_sum(sq);
+  if (lane == 0) red[warp] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < 8; ++w) t += red[w]; bc[1] = rsqrtf(t / (float)d + 1e-5f); }
+  __syncthreads();
+  const float rstd = bc[1];
+  if (threadIdx.x == 0) { stats[b * 2] = mean; stats[b * 2 + 1] = rstd; }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = threadIdx.x + 256 * i;
+    if (c < d) {
+      float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
+      if (thresh != 0) o = drop_keep(k0, k1, (uint64_t)b * d + c, thresh) ? o * scale : 0.f;
+      out[(int64_t)b * d + c] = o;
+    }
+  }
+}
+
+template <typename TT>
+__global__ void __launch_bounds__(256) img_pool_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ pooled,
+                                                           const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, TT* __restrict__ d_tokens,
+                                                           int n_tok, int d, int pool_cls, uint32_t thresh, float scale, uint32_t k0, uint32_t k1) {
+  __shared__ float red[2][8];
+  __shared__ float bc[2];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float mean = stats[b * 2], rstd = stats[b * 2 + 1];
+  float xh[4], dg[4];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = threadIdx.x + 256 * i;
+    xh[i] = dg[i] = 0.f;
+    if (c < d) {
+      float dy = dout[(int64_t)b * d + c];
+      if (thresh != 0) dy = drop_keep(k0, k1, (uint64_t)b * d + c, thresh) ? dy * scale : 0.f;
+      xh[i] = (pooled[(int64_t)b * d + c] - mean) * rstd;
+      dg[i] = dy * gamma[c];
+      s1 += dg[i]; s2 += dg[i] * xh[i];
+      atomicAdd(dgamma + c, dy * xh[i]);
+      atomicAdd(dbeta + c, dy);
+    }
+  }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t1 = 0.f, t2 = 0.f;
+    for (int w = 0; w < 8; ++w) { t1 += red[0][w]; t2 += red[1][w]; }
+    bc[0] = t1 / (float)d; bc[1] = t2 / (float)d;
+  }
+  __syncthreads();
+  if (d_tokens == nullptr) return;
+  TT* dt = d_tokens + (int64_t)b * n_tok * d;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = threadIdx.x + 256 * i;
+    if (c < d) {
+      const float dp = rstd * (dg[i] - bc[0] - xh[i] * bc[1]);
+      if (pool_cls) {
+        dt[c] = from_f<TT>(dp);
+        for (int t = 1; t < n_tok; ++t) dt[(int64_t)t * d + c] = from_f<TT>(0.f);
+      } else {
+        const TT o = from_f<TT>(dp / (float)n_tok);
+        for (int t = 0; t < n_tok; ++t) dt[(int64_t)t * d + c] = o;
+      }
+    }
+  }
+}
+
+struct ProjSaved { void *xt, *z, *h; };
+static ProjSaved proj_layout(Arena& A, int B, int d, int dtype) {
+  ProjSaved s; const size_t es = dtype_size(dtype), Bz = (size_t)B;
+  s.xt = A.take(Bz * d * es); s.z = A.take(Bz * 2 * d * es); s.h = A.take(Bz * 2 * d * es);
+  return s;
+}
+struct ProjScratch { void *g, *dz; };
+static ProjScratch proj_scratch(Arena& A, int B, int d, int proj, int dtype) {
+  ProjScratch t; const size_t es = dtype_size(dtype), Bz = (size_t)B;
+  t.g = A.take(Bz * proj * es); t.dz = A.take(Bz * 2 * d * es);
+  return t;
+}
+
+}  // namespace mmoe
+
+using namespace mmoe;
+
+extern "C" int mmoe_img_pool_fwd(const mmoe_call* c, const void* tokens, int tok_dtype, int32_t n_tok, int32_t d, int32_t pool_cls,
+                                 float* out, float* stats, float* pooled) {
+  if (c->B == 0) return 0;
+  MMOE_CHECK(d <= 1024, "img_pool: d must be <= 1024");
+  cudaStream_t st = (cudaStream_t)c->stream;
+  const float p = c->training ? c->drop_p : 0.f;
+  uint32_t k0, k1;
+  site_keys(c->seed, 0, &k0, &k1);
+  const uint32_t th = p > 0.f ? drop_threshold(p) : 0u;
+  const float sc = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const float* gamma = (const float*)c->params[0];
+  const float* beta = (const float*)c->params[1];
+  if (tok_dtype == MMOE_F32) img_pool_fwd_kernel<float><<<c->B, 256, 0, st>>>((const float*)tokens, gamma, beta, out, stats, pooled, n_tok, d, pool_cls, th, sc, k0, k1);
+  else if (tok_dtype == MMOE_BF16) img_pool_fwd_kernel<__nv_bfloat16><<<c->B, 256, 0, st>>>((const __nv_bfloat16*)tokens, gamma, beta, out, stats, pooled, n_tok, d, pool_cls, th, sc, k0, k1);
+  else img_pool_fwd_kernel<__half><<<c->B, 256, 0, st>>>((const __half*)tokens, gamma, beta, out, stats, pooled, n_tok, d, pool_cls, th, sc, k0, k1);
+  MMOE_LAUNCH_OK("img_pool_fwd_kernel");
+  return 0;
+}
+
+extern "C" int mmoe_img_pool_bwd(const mmoe_call* c, int32_t n_tok, int32_t d, int32_t pool_cls, const float* stats, const float* pooled,
+                                 const float* dout, void* d_tokens, int tok_dtype) {
+  if (c->B == 0) return 0;
+  cudaStream_t st = (cudaStream_t)c->stream;
+  const float p = c->training ? c->drop_p : 0.f;
+  uint32_t k0, k1;
+  site_keys(c->seed, 0, &k0, &k1);
+  const uint32_t th = p > 0.f ? drop_threshold(p) : 0u;
+  const float sc = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const float* gamma = (const float*)c->params[0];
+  float* dgamma = (float*)c->grads[0];
+  float* dbeta = (float*)c->grads[1];
+  if (tok_dtype == MMOE_F32) img_pool_bwd_kernel<float><<<c->B, 256, 0, st>>>(dout, pooled, stats, gamma, dgamma, dbeta, (float*)d_tokens, n_tok, d, pool_cls, th, sc, k0, k1);
+  else if (tok_dtype == MMOE_BF16) img_pool_bwd_kernel<__nv_bfloat16><<<c->B, 256, 0, st>>>(dout, pooled, stats, gamma, dgamma, dbeta, (__nv_bfloat16*)d_tokens, n_tok, d, pool_cls, th, sc, k0, k1);
+  else img_pool_bwd_kernel<__half><<<c->B, 256, 0, st>>>(dout, pooled, stats, gamma, dgamma, dbeta, (__half*)d_tokens, n_tok, d, pool_cls, th, sc, k0, k1);
+  MMOE_LAUNCH_OK("img_pool_bwd_kernel");
+  return 0;
+}
+
+extern "C" size_t mmoe_img_proj_saved_bytes(int32_t B, int32_t d, int32_t proj, int dtype) {
+  Arena A(nullptr);
+  proj_layout(A, B, d, dtype);
+  return A.off + 256;
+}
+extern "C" size_t mmoe_img_proj_workspace_bytes(int32_t B, int32_t d, int32_t proj, int dtype) {
+  Arena A(nullptr);
+  proj_scratch(A, B, d, proj, dtype);
+  return A.off + 256;
+}
+
+// params: {0.weight [2d,d] T, 0.bias, 2.weight [proj,2d] T, 2.bias}
+extern "C" int mmoe_img_proj_fwd(const mmoe_call* c, int32_t d, int32_t proj, const float* img_vec, float* out) {
+  if (c->B == 0) return 0;
+  const int B = c->B, dtype = c->dtype;
+  cudaStream_t st = (cudaStream_t)c->stream;
+  MMOE_CHECK(c->saved != nullptr && c->saved_bytes >= mmoe_img_proj_saved_bytes(B, d, proj, dtype), "img_proj_fwd: saved blob too small");
+  Arena A(c->saved);
+  ProjSaved s = proj_layout(A, B, d, dtype);
+  const void* const* P = c->params;
+  MMOE_TRY(cast_f32(img_vec, s.xt, (int64_t)B * d, dtype, st));
+  {
+    mmoe_epilogue e = epi_none();
+    e.out = s.h; e.out_dtype = dtype; e.ldo = 2 * d; e.bias = (const float*)P[1]; e.act = 2; e.preact = s.z;
+    mmoe_gemm_problem p = linear_fwd(s.xt, d, P[0], B, 2 * d, d, e);
+    MMOE_TRY(gemm_grouped(&p, 1, dtype, 0, st));
+  }
+  {
+    mmoe_epilogue e = epi_none();
+    e.out = out; e.out_dtype = MMOE_F32; e.ldo = proj; e.bias = (const float*)P[3];
+    mmoe_gemm_problem p = linear_fwd(s.h, 2 * d, P[2], B, proj, 2 * d, e);
+    MMOE_TRY(gemm_grouped(&p, 1, dtype, 0, st));
+  }
+  return 0;
+}
+
+extern "C" int mmoe_img_proj_bwd(const mmoe_call* c, int32_t d, int32_t proj, const float* dout, float* d_img_vec) {
+  if (c->B == 0) return 0;
+  const int B = c->B, dtype = c->dtype;
+  cudaStream_t st = (cudaStream_t)c->stream;
+  MMOE_CHECK(c->saved != nullptr && c->saved_bytes >= mmoe_img_proj_saved_bytes(B, d, proj, dtype), "img_proj_bwd: saved blob too small");
+  MMOE_CHECK(c->workspace != nullptr && c->workspace_bytes >= mmoe_img_proj_workspace_bytes(B, d, proj, dtype), "img_proj_bwd: workspace too small");
+  Arena A(c->saved);
+  ProjSaved s = proj_layout(A, B, d, dtype);
+  Arena W(c->workspace);
+  ProjScratch t = proj_scratch(W, B, d, proj, dtype);
+  const void* const* P = c->params;
+  void* const* G = c->grads;
+  MMOE_TRY(cast_drop_colsum(dout, t.g, (float*)G[3], B, proj, 0.f, 0, 0, dtype, st));
+  {
+    mmoe_epilogue e = epi_none();
+    e.out = t.dz; e.out_dtype = dtype; e.ldo = 2 * d; e.bwd_mode = 2; e.aux = s.z; e.ld_aux = 2 * d; e.colsum = (float*)G[1];
+    mmoe_gemm_problem p[2] = {linear_dgrad(t.g, proj, P[2], B, proj, 2 * d, e), linear_wgrad(t.g, proj, s.h, 2 * d, (float*)G[2], B, proj, 2 * d)};
+    MMOE_TRY(gemm_grouped(p, 2, dtype, 0, st));
+  }
+  {
+    mmoe_epilogue e = epi_none();
+    e.out = d_img_vec; e.out_dtype = MMOE_F32; e.ldo = d;
+    mmoe_gemm_problem p[2] = {linear_dgrad(t.dz, 2 * d, P[0], B, 2 * d, d, e), linear_wgrad(t.dz, 2 * d, s.xt, d, (float*)G[0], B, 2 * d, d)};
+    MMOE_TRY(gemm_grouped(p, 2, dtype, 0, st));
+  }
+  return 0;
+}

@@ -1,0 +1,380 @@
+// Bandwidth-bound helper kernels: casts, dropout masks, LayerNorm forward/backward.
+// All rows are d <= 1024 wide (d = 768 on this path), d % 4 == 0; one warp owns a row and
+// moves it with 128-bit (fp32) / 64-bit (16-bit types) coalesced accesses.
+#include "kernels.cuh"
+
+namespace mmoe {
+
+thread_local char g_error[512] = {0};
+thread_local int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+
+// ---------------------------------------------------------------- vector load/store helpers
+template <typename T> __device__ __forceinline__ float4 load4(const T* p);
+template <> __device__ __forceinline__ float4 load4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+template <> __device__ __forceinline__ float4 load4<__half>(const __half* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __half2 a = *reinterpret_cast<const __half2*>(&u.x);
+  const __half2 b = *reinterpret_cast<const __half2*>(&u.y);
+  return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, float4 v);
+template <> __device__ __forceinline__ void store4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+template <> __device__ __forceinline__ void store4<__half>(__half* p, float4 v) {
+  __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// ---------------------------------------------------------------- cast
+template <typename T>
+__global__ void cast_kernel(const float* __restrict__ x, T* __restrict__ y, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n) {
+      store4<T>(y + i, load4<float>(x + i));
+    } else {
+      for (int64_t j = i; j < n; ++j) y[j] = from_f<T>(x[j]);
+    }
+  }
+}
+
+int cast_f32(const float* x, void* y, int64_t n, int dtype, cudaStream_t s) {
+  if (n == 0) return 0;
+  MMOE_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0, "cast: unaligned pointer");
+  const int threads = 256;
+  int64_t blocks = (n / 4 + threads - 1) / threads;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (dtype == MMOE_BF16) cast_kernel<__nv_bfloat16><<<(int)blocks, threads, 0, s>>>(x, (__nv_bfloat16*)y, n);
+  else if (dtype == MMOE_F16) cast_kernel<__half><<<(int)blocks, threads, 0, s>>>(x, (__half*)y, n);
+  else cast_kernel<float><<<(int)blocks, threads, 0, s>>>(x, (float*)y, n);
+  MMOE_LAUNCH_OK("cast_kernel");
+  return 0;
+}
+
+// ---------------------------------------------------------------- cast + dropout + column sums
+// block = 256 threads, owns a panel of 32 rows; thread t owns 4 columns (c = 4t + 1024*j)
+template <typename T>
+__global__ void cast_drop_colsum_kernel(const float* __restrict__ x, T* __restrict__ g, float* __restrict__ colsum,
+                                        int64_t rows, int cols, uint32_t thresh, float scale, uint32_t k0, uint32_t k1) {
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int64_t r1 = min(rows, r0 + 32);
+  for (int c = threadIdx.x * 4; c < cols; c += blockDim.x * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t r = r0; r < r1; ++r) {
+      float4 v = load4<float>(x + r * cols + c);
+      if (thresh != 0) {
+        const uint64_t idx = (uint64_t)r * cols + c;
+        v.x = drop_keep(k0, k1, idx + 0, thresh) ? v.x * scale : 0.f;
+        v.y = drop_keep(k0, k1, idx + 1, thresh) ? v.y * scale : 0.f;
+        v.z = drop_keep(k0, k1, idx + 2, thresh) ? v.z * scale : 0.f;
+        v.w = drop_keep(k0, k1, idx + 3, thresh) ? v.w * scale : 0.f;
+      }
+      if (g != nullptr) {
+        store4<T>(g + r * cols + c, v);
+        // column sums are taken over the values as stored (rounded to T)
+        const float4 w = load4<T>(g + r * cols + c);
+        v = w;
+      }
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (colsum != nullptr) {
+      atomicAdd(colsum + c + 0, acc.x); atomicAdd(colsum + c + 1, acc.y);
+      atomicAdd(colsum + c + 2, acc.z); atomicAdd(colsum + c + 3, acc.w);
+    }
+  }
+}
+
+int cast_drop_colsum(const float* x, void* g, float* colsum, int64_t rows, int cols, float drop_p, uint32_t k0, uint32_t k1,
+                     int dtype, cudaStream_t s) {
+  if (rows == 0) return 0;
+  MMOE_CHECK(cols % 4 == 0, "cast_drop_colsum: cols must be a multiple of 4");
+  const uint32_t thresh = drop_p > 0.f ? drop_threshold(drop_p) : 0u;
+  const float scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const int blocks = (int)((rows + 31) / 32);
+  if (dtype == MMOE_BF16) cast_drop_colsum_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(x, (__nv_bfloat16*)g, colsum, rows, cols, thresh, scale, k0, k1);
+  else if (dtype == MMOE_F16) cast_drop_colsum_kernel<__half><<<blocks, 256, 0, s>>>(x, (__half*)g, colsum, rows, cols, thresh, scale, k0, k1);
+  else cast_drop_colsum_kernel<float><<<blocks, 256, 0, s>>>(x, (float*)g, colsum, rows, cols, thresh, scale, k0, k1);
+  MMOE_LAUNCH_OK("cast_drop_colsum_kernel");
+  return 0;
+}
+
+// ---------------------------------------------------------------- dropout mask (debug/test)
+__global__ void dropout_mask_kernel(uint32_t k0, uint32_t k1, uint32_t thresh, int64_t n, uint8_t* out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = drop_keep(k0, k1, (uint64_t)i, thresh) ? 1 : 0;
+}
+int dropout_mask(uint32_t k0, uint32_t k1, float p, int64_t n, uint8_t* out, cudaStream_t s) {
+  if (n == 0) return 0;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 4096) blocks = 4096;
+  dropout_mask_kernel<<<(int)blocks, 256, 0, s>>>(k0, k1, p > 0.f ? drop_threshold(p) : 0u, n, out);
+  MMOE_LAUNCH_OK("dropout_mask_kernel");
+  return 0;
+}
+
+// ---------------------------------------------------------------- LayerNorm forward
+constexpr int LN_NV = 8;   // float4 per lane -> d <= 1024
+
+template <typename XT, typename T>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const XT* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, T* __restrict__ y_t,
+                                                     float* __restrict__ y_f, float* __restrict__ stats, int64_t rows, int d) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float inv_d = 1.0f / (float)d;
+  for (int64_t row = warp0; row < rows; row += nwarps) {
+    const XT* xr = x + row * d;
+    float4 v[LN_NV];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) { v[i] = load4<XT>(xr + c); sum += v[i].x + v[i].y + v[i].z + v[i].w; }
+      else v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float mean = warp_sum(sum) * inv_d;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) {
+        const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
+        sq += a * a + b * b + e * e + f * f;
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * inv_d + 1e-5f);
+    if (stats != nullptr && lane == 0) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
+#pragma unroll
+    for (int i = 0; i < LN_NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) {
+        const float4 g = load4<float>(gamma + c), b = load4<float>(beta + c);
+        float4 o;
+        o.x = (v[i].x - mean) * rstd * g.x + b.x;
+        o.y = (v[i].y - mean) * rstd * g.y + b.y;
+        o.z = (v[i].z - mean) * rstd * g.z + b.z;
+        o.w = (v[i].w - mean) * rstd * g.w + b.w;
+        if (y_t != nullptr) store4<T>(y_t + row * d + c, o);
+        if (y_f != nullptr) store4<float>(y_f + row * d + c, o);
+      }
+    }
+  }
+}
+
+template <typename T>
+static int ln_fwd_dispatch(const void* x, bool x_f32, const float* gamma, const float* beta, void* y_t, float* y_f, float* stats,
+                           int64_t rows, int d, cudaStream_t s) {
+  int64_t blocks = (rows + 7) / 8;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (x_f32) ln_fwd_kernel<float, T><<<(int)blocks, 256, 0, s>>>((const float*)x, gamma, beta, (T*)y_t, y_f, stats, rows, d);
+  else       ln_fwd_kernel<T, T><<<(int)blocks, 256, 0, s>>>((const T*)x, gamma, beta, (T*)y_t, y_f, stats, rows, d);
+  MMOE_LAUNCH_OK("ln_fwd_kernel");
+  return 0;
+}
+
+int layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, void* y_t, float* y_f32, float* stats,
+                  int64_t rows, int d, int dtype, cudaStream_t s) {
+  if (rows == 0) return 0;
+  MMOE_CHECK(d % 4 == 0 && d <= LN_NV * 128, "layernorm: d must be a multiple of 4 and <= %d (got %d)", LN_NV * 128, d);
+  MMOE_CHECK(x_dtype == MMOE_F32 || x_dtype == dtype, "layernorm: x must be fp32 or the operand dtype");
+  const bool xf = x_dtype == MMOE_F32;
+  if (dtype == MMOE_BF16) return ln_fwd_dispatch<__nv_bfloat16>(x, xf, gamma, beta, y_t, y_f32, stats, rows, d, s);
+  if (dtype == MMOE_F16) return ln_fwd_dispatch<__half>(x, xf, gamma, beta, y_t, y_f32, stats, rows, d, s);
+  return ln_fwd_dispatch<float>(x, true, gamma, beta, y_t, y_f32, stats, rows, d, s);
+}
+
+// ---------------------------------------------------------------- LayerNorm backward
+struct LnBwdDev {
+  const void* dy; const void* x; const float* stats; const float* gamma; const float* dres;
+  float* dx; float* dgamma; float* dbeta; void* g_out; float* g_colsum;
+  uint32_t thresh, k0, k1; float scale;
+  int64_t rows; int d;
+};
+
+template <typename DT_, typename XT, typename T>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdDev a) {
+  __shared__ float red[8][LN_NV * 128];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp0 = (int64_t)blockIdx.x * 8 + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  const int d = a.d;
+  const float inv_d = 1.0f / (float)d;
+  float4 acc_g[LN_NV], acc_b[LN_NV], acc_c[LN_NV];
+#pragma unroll
+  for (int i = 0; i < LN_NV; ++i) acc_g[i] = acc_b[i] = acc_c[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const DT_* dy = reinterpret_cast<const DT_*>(a.dy);
+  const XT* x = reinterpret_cast<const XT*>(a.x);
+  T* gout = reinterpret_cast<T*>(a.g_out);
+  for (int64_t row = warp0; row < a.rows; row += nwarps) {
+    const float mean = a.stats[row * 2], rstd = a.stats[row * 2 + 1];
+    float4 xh[LN_NV], dg[LN_NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) {
+        const float4 xv = load4<XT>(x + row * d + c);
+        const float4 dv = load4<DT_>(dy + row * d + c);
+        const float4 g = load4<float>(a.gamma + c);
+        xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+        dg[i] = make_float4(dv.x * g.x, dv.y * g.y, dv.z * g.z, dv.w * g.w);
+        s1 += dg[i].x + dg[i].y + dg[i].z + dg[i].w;
+        s2 += dg[i].x * xh[i].x + dg[i].y * xh[i].y + dg[i].z * xh[i].z + dg[i].w * xh[i].w;
+        acc_g[i].x += dv.x * xh[i].x; acc_g[i].y += dv.y * xh[i].y; acc_g[i].z += dv.z * xh[i].z; acc_g[i].w += dv.w * xh[i].w;
+        acc_b[i].x += dv.x; acc_b[i].y += dv.y; acc_b[i].z += dv.z; acc_b[i].w += dv.w;
+      }
+    }
+    s1 = warp_sum(s1) * inv_d;
+    s2 = warp_sum(s2) * inv_d;
+#pragma unroll
+    for (int i = 0; i < LN_NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) {
+        float4 o;
+        o.x = rstd * (dg[i].x - s1 - xh[i].x * s2);
+        o.y = rstd * (dg[i].y - s1 - xh[i].y * s2);
+        o.z = rstd * (dg[i].z - s1 - xh[i].z * s2);
+        o.w = rstd * (dg[i].w - s1 - xh[i].w * s2);
+        if (a.dres != nullptr) {
+          const float4 r = load4<float>(a.dres + row * d + c);
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        if (a.dx != nullptr) store4<float>(a.dx + row * d + c, o);
+        if (gout != nullptr || a.g_colsum != nullptr) {
+          if (a.thresh != 0) {
+            const uint64_t idx = (uint64_t)row * d + c;
+            o.x = drop_keep(a.k0, a.k1, idx + 0, a.thresh) ? o.x * a.scale : 0.f;
+            o.y = drop_keep(a.k0, a.k1, idx + 1, a.thresh) ? o.y * a.scale : 0.f;
+            o.z = drop_keep(a.k0, a.k1, idx + 2, a.thresh) ? o.z * a.scale : 0.f;
+            o.w = drop_keep(a.k0, a.k1, idx + 3, a.thresh) ? o.w * a.scale : 0.f;
+          }
+          if (gout != nullptr) {
+            store4<T>(gout + row * d + c, o);
+            o = load4<T>(gout + row * d + c);
+          }
+          acc_c[i].x += o.x; acc_c[i].y += o.y; acc_c[i].z += o.z; acc_c[i].w += o.w;
+        }
+      }
+    }
+  }
+  // block reduction of the per-lane column partials, then one atomic per column per block
+  auto reduce_to = [&](float4 (&acc)[LN_NV], float* dst) {
+#pragma unroll
+    for (int i = 0; i < LN_NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) *reinterpret_cast<float4*>(&red[wib][c]) = acc[i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += 256) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w][c];
+      atomicAdd(dst + c, t);
+    }
+    __syncthreads();
+  };
+  if (a.dgamma != nullptr) { reduce_to(acc_g, a.dgamma); reduce_to(acc_b, a.dbeta); }
+  if (a.g_colsum != nullptr) reduce_to(acc_c, a.g_colsum);
+}
+
+template <typename T>
+static int ln_bwd_dispatch(const LnBwdDev& dev, bool dy_f32, bool x_f32, int blocks, cudaStream_t s) {
+  if (dy_f32 && x_f32)       ln_bwd_kernel<float, float, T><<<blocks, 256, 0, s>>>(dev);
+  else if (dy_f32 && !x_f32) ln_bwd_kernel<float, T, T><<<blocks, 256, 0, s>>>(dev);
+  else if (!dy_f32 && x_f32) ln_bwd_kernel<T, float, T><<<blocks, 256, 0, s>>>(dev);
+  else                       ln_bwd_kernel<T, T, T><<<blocks, 256, 0, s>>>(dev);
+  MMOE_LAUNCH_OK("ln_bwd_kernel");
+  return 0;
+}
+
+int layernorm_bwd(const LnBwdArgs& a, cudaStream_t s) {
+  if (a.rows == 0) return 0;
+  MMOE_CHECK(a.d % 4 == 0 && a.d <= LN_NV * 128, "layernorm_bwd: d must be a multiple of 4 and <= %d", LN_NV * 128);
+  MMOE_CHECK((a.dgamma == nullptr) == (a.dbeta == nullptr), "layernorm_bwd: dgamma and dbeta go together");
+  LnBwdDev dev;
+  dev.dy = a.dy; dev.x = a.x; dev.stats = a.stats; dev.gamma = a.gamma; dev.dres = a.dres;
+  dev.dx = a.dx; dev.dgamma = a.dgamma; dev.dbeta = a.dbeta; dev.g_out = a.g_out; dev.g_colsum = a.g_colsum;
+  dev.thresh = a.drop_p > 0.f ? drop_threshold(a.drop_p) : 0u;
+  dev.scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+  dev.k0 = a.k0; dev.k1 = a.k1; dev.rows = a.rows; dev.d = a.d;
+  int64_t blocks = (a.rows + 7) / 8;
+  const int64_t cap = (int64_t)sm_count() * 2;
+  if (blocks > cap) blocks = cap;
+  MMOE_CHECK((a.dy_dtype == MMOE_F32 || a.dy_dtype == a.dtype) && (a.x_dtype == MMOE_F32 || a.x_dtype == a.dtype),
+             "layernorm_bwd: dy and x must be fp32 or the operand dtype");
+  const bool df = a.dy_dtype == MMOE_F32, xf = a.x_dtype == MMOE_F32;
+  if (a.dtype == MMOE_BF16) return ln_bwd_dispatch<__nv_bfloat16>(dev, df, xf, (int)blocks, s);
+  if (a.dtype == MMOE_F16) return ln_bwd_dispatch<__half>(dev, df, xf, (int)blocks, s);
+  return ln_bwd_dispatch<float>(dev, true, true, (int)blocks, s);
+}
+
+}  // namespace mmoe
+
+// ---------------------------------------------------------------- C ABI (elementary ops)
+using namespace mmoe;
+
+extern "C" int mmoe_abi_version(void) { return MMOE_ABI_VERSION; }
+extern "C" size_t mmoe_abi_sizeof(int which) {
+  switch (which) {
+    case 0: return sizeof(mmoe_epilogue);
+    case 1: return sizeof(mmoe_gemm_problem);
+    case 2: return sizeof(mmoe_call);
+    case 3: return sizeof(mmoe_head_cfg);
+    case 4: return sizeof(mmoe_cross_cfg);
+    case 5: return sizeof(mmoe_fuse_cfg);
+    case 6: return sizeof(mmoe_home_cfg);
+    default: return 0;
+  }
+}
+extern "C" const char* mmoe_last_error(void) { return mmoe::g_error; }
+extern "C" int64_t mmoe_launch_count(int reset) {
+  const int64_t n = mmoe::g_launches;
+  if (reset) mmoe::g_launches = 0;
+  return n;
+}
+extern "C" int mmoe_init(void) {
+  int dev = 0;
+  MMOE_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  MMOE_CUDA(cudaGetDeviceProperties(&prop, dev));
+  MMOE_CHECK(prop.major == 10, "this library is built for sm_100a only; device %d is sm_%d%d (%s)", dev, prop.major, prop.minor, prop.name);
+  return 0;
+}
+extern "C" int mmoe_cast_f32(const float* x, void* y, int64_t n, int dtype, void* stream) {
+  return cast_f32(x, y, n, dtype, (cudaStream_t)stream);
+}
+extern "C" int mmoe_dropout_mask(uint32_t key0, uint32_t key1, float p, int64_t n, uint8_t* out, void* stream) {
+  return dropout_mask(key0, key1, p, n, out, (cudaStream_t)stream);
+}
+extern "C" int mmoe_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, void* y_t, float* y_f32,
+                                  float* stats, int64_t rows, int32_t d, int dtype, void* stream) {
+  return layernorm_fwd(x, x_dtype, gamma, beta, y_t, y_f32, stats, rows, d, dtype, (cudaStream_t)stream);
+}

@@ -1,0 +1,345 @@
+"""torch.autograd.Function wrappers over the C ABI (include/mmoe_b200.h).
+
+PyTorch is used here for device memory (tensors as buffers), streams and autograd
+bookkeeping only; every arithmetic step of the path runs in libmmoe_b200.so.
+There is no CPU / eager fallback: non-CUDA inputs raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from ._lib import BF16, F16, F32, Call, CrossCfg, FuseCfg, HeadCfg, HomeCfg, check, lib, ptr_array
+
+_TORCH2MMOE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
+_MMOE2TORCH = {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}
+
+
+def compute_dtype() -> int:
+    """fp32 unless a CUDA autocast region is active, then its 16-bit dtype (the reference
+    scripts use torch.cuda.amp.autocast() = fp16; BASELINE's bf16 configs pass dtype=bfloat16)."""
+    if torch.is_autocast_enabled("cuda"):
+        dt = torch.get_autocast_dtype("cuda")
+        if dt in (torch.bfloat16, torch.float16):
+            return _TORCH2MMOE[dt]
+    return F32
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("mmoe_b200 runs on CUDA (sm_100a) only; got a tensor on %s — there is no CPU fallback" % t.device)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(x: torch.Tensor) -> torch.Tensor:
+    return x.detach().to(torch.float32).contiguous()
+
+
+def _new_seed(training: bool, p: float) -> int:
+    if not training or p <= 0.0:
+        return 0
+    # drawn from torch's CPU generator: reproducible under torch.manual_seed, no device sync
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+class ParamPack:
+    """Device pointers of a module's parameters in state_dict order.
+
+    2-D GEMM weights are handed to the library in the compute dtype; the 16-bit copies
+    are produced by the library's cast kernel and cached until the parameter is updated
+    in place (optimizer step) — detected through the tensor's version counter.
+    """
+
+    def __init__(self, names: Sequence[str], lowp: Sequence[str]):
+        self.names = list(names)
+        self.lowp = set(lowp)
+        self._cache = {}
+
+    def tensors(self, params: Sequence[torch.Tensor], dtype: int) -> List[torch.Tensor]:
+        out = []
+        L = lib()
+        for name, p in zip(self.names, params):
+            _require_cuda(p)
+            if p.dtype != torch.float32:
+                raise RuntimeError(f"parameter {name} must be float32 (got {p.dtype})")
+            pd = p.detach()
+            if not pd.is_contiguous():
+                pd = pd.contiguous()
+            if dtype == F32 or name not in self.lowp:
+                out.append(pd)
+                continue
+            key = (name, dtype)
+            ent = self._cache.get(key)
+            if ent is None or ent[0] != p._version or ent[1] != pd.data_ptr() or ent[2].device != pd.device:
+                q = torch.empty(pd.shape, dtype=_MMOE2TORCH[dtype], device=pd.device)
+                check(L.mmoe_cast_f32(pd.data_ptr(), q.data_ptr(), pd.numel(), dtype, _stream()), "cast")
+                ent = (p._version, pd.data_ptr(), q)
+                self._cache[key] = ent
+            out.append(ent[2])
+        return out
+
+
+def _alloc_grads(params: Sequence[torch.Tensor], used: Sequence[bool]):
+    """One zeroed fp32 buffer holding the gradients of all used parameters; returns (views, pointer list)."""
+    total = sum(p.numel() + 64 for p, u in zip(params, used) if u)
+    flat = torch.zeros(max(total, 1), dtype=torch.float32, device=params[0].device)
+    views, ptrs, off = [], [], 0
+    for p, u in zip(params, used):
+        if not u:
+            views.append(None)
+            ptrs.append(None)
+            continue
+        v = flat[off:off + p.numel()].view(p.shape)
+        off += (p.numel() + 63) // 64 * 64
+        views.append(v)
+        ptrs.append(v.data_ptr())
+    return views, ptrs
+
+
+def _bytes(n: int, device) -> torch.Tensor:
+    return torch.empty(max(int(n), 1), dtype=torch.uint8, device=device)
+
+
+def _call(dtype, B, training, home, drop_p, seed, ptensors, grad_ptrs, saved, workspace) -> Call:
+    c = Call()
+    c.dtype, c.B, c.training, c.home = dtype, B, int(training), int(home)
+    c.drop_p, c.seed = float(drop_p), int(seed)
+    pa = ptr_array([t.data_ptr() for t in ptensors])
+    c.params = C.cast(pa, C.POINTER(C.c_void_p))
+    c._keep = [pa, ptensors]
+    if grad_ptrs is not None:
+        ga = ptr_array(grad_ptrs)
+        c.grads = C.cast(ga, C.POINTER(C.c_void_p))
+        c._keep.append(ga)
+    if saved is not None:
+        c.saved, c.saved_bytes = saved.data_ptr(), saved.numel()
+    if workspace is not None:
+        c.workspace, c.workspace_bytes = workspace.data_ptr(), workspace.numel()
+    c.stream = _stream()
+    return c
+
+
+# ----------------------------------------------------------------------------------------------
+# TwoTaskMMoE / HOME_MMoE_Complete
+# ----------------------------------------------------------------------------------------------
+class HeadFn(torch.autograd.Function):
+    """logits[2,B] = head(expert_vecs[B,n,d]).  kind: 'mmoe' (model.py:562-577) or 'home' (model_HoME.py:590-638)."""
+
+    @staticmethod
+    def forward(ctx, pack: ParamPack, kind: str, cfg, training: bool, drop_p: float, want_gates: bool,
+                expert_vecs: torch.Tensor, *params: torch.Tensor):
+        _require_cuda(expert_vecs)
+        L = lib()
+        dtype = compute_dtype()
+        ev = _f32c(expert_vecs)
+        B, dev = ev.shape[0], ev.device
+        pt = pack.tensors(params, dtype)
+        fwd, bwd, sb, wb = ((L.mmoe_head_fwd, L.mmoe_head_bwd, L.mmoe_head_saved_bytes, L.mmoe_head_workspace_bytes) if kind == "mmoe"
+                            else (L.mmoe_home_fwd, L.mmoe_home_bwd, L.mmoe_home_saved_bytes, L.mmoe_home_workspace_bytes))
+        saved = _bytes(sb(C.byref(cfg), B, dtype), dev)
+        logits = torch.empty((2, B), dtype=torch.float32, device=dev)
+        n_gate = cfg.n_expert if kind == "mmoe" else cfg.n_shared + cfg.n_task
+        gates = torch.empty((2, B, n_gate), dtype=torch.float32, device=dev) if want_gates else None
+        seed = _new_seed(training, drop_p)
+        c = _call(dtype, B, training, 0, drop_p, seed, pt, None, saved, None)
+        check(fwd(C.byref(c), C.byref(cfg), ev.data_ptr(), logits.data_ptr(), gates.data_ptr() if want_gates else None), kind + "_fwd")
+        ctx.state = (pack, kind, cfg, training, drop_p, seed, dtype, ev, pt, saved, bwd, wb)
+        ctx.n_params = len(params)
+        ctx.param_req = [p.requires_grad for p in params]
+        ctx.in_dtype = expert_vecs.dtype
+        ctx.mark_non_differentiable(*( [gates] if want_gates else [] ))
+        if want_gates:
+            return logits, gates
+        return logits
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dlogits, *unused):
+        pack, kind, cfg, training, drop_p, seed, dtype, ev, pt, saved, bwd, wb = ctx.state
+        L = lib()
+        B, dev = ev.shape[0], ev.device
+        views, gptrs = _alloc_grads(pt_shapes(pt, ctx), [True] * ctx.n_params)
+        work = _bytes(wb(C.byref(cfg), B, dtype), dev)
+        d_ev = torch.empty_like(ev)
+        dl = _f32c(dlogits)
+        c = _call(dtype, B, training, 0, drop_p, seed, pt, gptrs, saved, work)
+        check(bwd(C.byref(c), C.byref(cfg), ev.data_ptr(), dl.data_ptr(), d_ev.data_ptr()), kind + "_bwd")
+        grads = [v if req else None for v, req in zip(views, ctx.param_req)]
+        return (None, None, None, None, None, None, d_ev.to(ctx.in_dtype), *grads)
+
+
+def pt_shapes(pt, ctx):
+    """fp32 gradient buffers have the shapes of the parameters (pt holds same-shaped tensors)."""
+    return pt
+
+
+# ----------------------------------------------------------------------------------------------
+# RobustTextCrossExpert
+# ----------------------------------------------------------------------------------------------
+class CrossFn(torch.autograd.Function):
+    """out[B,d] = cross(user[B,S,d], user_mask[B,S], item[B,S,d], item_mask[B,S]) — model.py:426-451
+    (home=True: model_HoME.py:441-466)."""
+
+    @staticmethod
+    def forward(ctx, pack: ParamPack, cfg: CrossCfg, home: bool, used: Sequence[bool], training: bool, drop_p: float,
+                user, user_mask, item, item_mask, *params):
+        _require_cuda(user, user_mask, item, item_mask)
+        L = lib()
+        dtype = compute_dtype()
+        u, it = _f32c(user), _f32c(item)
+        um = user_mask.detach().to(torch.bool).contiguous().view(torch.uint8)
+        im = item_mask.detach().to(torch.bool).contiguous().view(torch.uint8)
+        B, dev = u.shape[0], u.device
+        pt = pack.tensors(params, dtype)
+        saved = _bytes(L.mmoe_cross_saved_bytes(C.byref(cfg), B, dtype), dev)
+        out = torch.empty((B, cfg.d), dtype=torch.float32, device=dev)
+        seed = _new_seed(training, drop_p)
+        c = _call(dtype, B, training, home, drop_p, seed, pt, None, saved, None)
+        check(L.mmoe_cross_fwd(C.byref(c), C.byref(cfg), u.data_ptr(), um.data_ptr(), it.data_ptr(), im.data_ptr(), out.data_ptr()), "cross_fwd")
+        ctx.state = (cfg, home, list(used), training, drop_p, seed, dtype, u, um, it, im, pt, saved)
+        ctx.param_req = [p.requires_grad for p in params]
+        ctx.in_dtypes = (user.dtype, item.dtype)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        cfg, home, used, training, drop_p, seed, dtype, u, um, it, im, pt, saved = ctx.state
+        L = lib()
+        B, dev = u.shape[0], u.device
+        views, gptrs = _alloc_grads(pt, used)
+        work = _bytes(L.mmoe_cross_workspace_bytes(C.byref(cfg), B, dtype), dev)
+        d_user, d_item = torch.empty_like(u), torch.empty_like(it)
+        do = _f32c(dout)
+        c = _call(dtype, B, training, home, drop_p, seed, pt, gptrs, saved, work)
+        check(L.mmoe_cross_bwd(C.byref(c), C.byref(cfg), u.data_ptr(), um.data_ptr(), it.data_ptr(), im.data_ptr(), do.data_ptr(),
+                               d_user.data_ptr(), d_item.data_ptr()), "cross_bwd")
+        grads = [v if (req and v is not None) else None for v, req in zip(views, ctx.param_req)]
+        return (None, None, None, None, None, None, d_user.to(ctx.in_dtypes[0]), None, d_item.to(ctx.in_dtypes[1]), None, *grads)
+
+
+# ----------------------------------------------------------------------------------------------
+# EnhancedCrossFuse
+# ----------------------------------------------------------------------------------------------
+class FuseFn(torch.autograd.Function):
+    """out[B,d] = fuse(v_cls[B,d], t_cls[B,d]) — model.py:491-507 (home=True: model_HoME.py:506-522)."""
+
+    @staticmethod
+    def forward(ctx, pack: ParamPack, cfg: FuseCfg, home: bool, used: Sequence[bool], training: bool, drop_p: float,
+                v_cls, t_cls, *params):
+        _require_cuda(v_cls, t_cls)
+        L = lib()
+        dtype = compute_dtype()
+        v, t = _f32c(v_cls), _f32c(t_cls)
+        B, dev = v.shape[0], v.device
+        pt = pack.tensors(params, dtype)
+        saved = _bytes(L.mmoe_fuse_saved_bytes(C.byref(cfg), B, dtype), dev)
+        out = torch.empty((B, cfg.d), dtype=torch.float32, device=dev)
+        seed = _new_seed(training, drop_p)
+        c = _call(dtype, B, training, home, drop_p, seed, pt, None, saved, None)
+        check(L.mmoe_fuse_fwd(C.byref(c), C.byref(cfg), v.data_ptr(), t.data_ptr(), out.data_ptr()), "fuse_fwd")
+        ctx.state = (cfg, home, list(used), training, drop_p, seed, dtype, B, dev, pt, saved)
+        ctx.param_req = [p.requires_grad for p in params]
+        ctx.in_dtypes = (v_cls.dtype, t_cls.dtype)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        cfg, home, used, training, drop_p, seed, dtype, B, dev, pt, saved = ctx.state
+        L = lib()
+        views, gptrs = _alloc_grads(pt, used)
+        work = _bytes(L.mmoe_fuse_workspace_bytes(C.byref(cfg), B, dtype), dev)
+        d_cat = torch.empty((B, 2, cfg.d), dtype=torch.float32, device=dev)
+        do = _f32c(dout)
+        c = _call(dtype, B, training, home, drop_p, seed, pt, gptrs, saved, work)
+        check(L.mmoe_fuse_bwd(C.byref(c), C.byref(cfg), do.data_ptr(), d_cat.data_ptr()), "fuse_bwd")
+        grads = [v if (req and v is not None) else None for v, req in zip(views, ctx.param_req)]
+        return (None, None, None, None, None, None, d_cat[:, 0].to(ctx.in_dtypes[0]), d_cat[:, 1].to(ctx.in_dtypes[1]), *grads)
+
+
+# ----------------------------------------------------------------------------------------------
+# ItemImageExpert tail (pool + LN + dropout) and the HoME projection head
+# ----------------------------------------------------------------------------------------------
+class ImgPoolFn(torch.autograd.Function):
+    """img_vec[B,d] = dropout(LN(pool(tokens[B,n_tok,d]))) — model.py:377-385."""
+
+    @staticmethod
+    def forward(ctx, pool_cls: bool, training: bool, drop_p: float, tokens, gamma, beta):
+        _require_cuda(tokens, gamma, beta)
+        L = lib()
+        tk = tokens.detach()
+        if tk.dtype not in _TORCH2MMOE:
+            tk = tk.float()
+        tk = tk.contiguous()
+        B, n_tok, d = tk.shape
+        dev = tk.device
+        g, b = _f32c(gamma), _f32c(beta)
+        out = torch.empty((B, d), dtype=torch.float32, device=dev)
+        stats = torch.empty((B, 2), dtype=torch.float32, device=dev)
+        pooled = torch.empty((B, d), dtype=torch.float32, device=dev)
+        seed = _new_seed(training, drop_p)
+        c = _call(F32, B, training, 0, drop_p, seed, [g, b], None, None, None)
+        check(L.mmoe_img_pool_fwd(C.byref(c), tk.data_ptr(), _TORCH2MMOE[tk.dtype], n_tok, d, int(pool_cls), out.data_ptr(),
+                                  stats.data_ptr(), pooled.data_ptr()), "img_pool_fwd")
+        ctx.state = (pool_cls, training, drop_p, seed, g, b, stats, pooled, tk.dtype, tuple(tk.shape), tokens.dtype)
+        ctx.needs_tokens = tokens.requires_grad
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        pool_cls, training, drop_p, seed, g, b, stats, pooled, tk_dtype, shape, in_dtype = ctx.state
+        L = lib()
+        B, n_tok, d = shape
+        dev = dout.device
+        dg, db = torch.zeros_like(g), torch.zeros_like(b)
+        d_tok = torch.empty(shape, dtype=tk_dtype, device=dev) if ctx.needs_tokens else None
+        do = _f32c(dout)
+        c = _call(F32, B, training, 0, drop_p, seed, [g, b], [dg.data_ptr(), db.data_ptr()], None, None)
+        check(L.mmoe_img_pool_bwd(C.byref(c), n_tok, d, int(pool_cls), stats.data_ptr(), pooled.data_ptr(), do.data_ptr(),
+                                  d_tok.data_ptr() if d_tok is not None else None, _TORCH2MMOE[tk_dtype]), "img_pool_bwd")
+        return None, None, None, (d_tok.to(in_dtype) if d_tok is not None else None), dg, db
+
+
+class ImgProjFn(torch.autograd.Function):
+    """projected[B,proj] = Linear(GELU(Linear(img_vec))) — model_HoME.py:383-387,397."""
+
+    @staticmethod
+    def forward(ctx, pack: ParamPack, d: int, proj: int, img_vec, *params):
+        _require_cuda(img_vec)
+        L = lib()
+        dtype = compute_dtype()
+        x = _f32c(img_vec)
+        B, dev = x.shape[0], x.device
+        pt = pack.tensors(params, dtype)
+        saved = _bytes(L.mmoe_img_proj_saved_bytes(B, d, proj, dtype), dev)
+        out = torch.empty((B, proj), dtype=torch.float32, device=dev)
+        c = _call(dtype, B, False, 0, 0.0, 0, pt, None, saved, None)
+        check(L.mmoe_img_proj_fwd(C.byref(c), d, proj, x.data_ptr(), out.data_ptr()), "img_proj_fwd")
+        ctx.state = (d, proj, dtype, B, dev, pt, saved)
+        ctx.param_req = [p.requires_grad for p in params]
+        ctx.in_dtype = img_vec.dtype
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        d, proj, dtype, B, dev, pt, saved = ctx.state
+        L = lib()
+        views, gptrs = _alloc_grads(pt, [True] * len(pt))
+        work = _bytes(L.mmoe_img_proj_workspace_bytes(B, d, proj, dtype), dev)
+        dx = torch.empty((B, d), dtype=torch.float32, device=dev)
+        do = _f32c(dout)
+        c = _call(dtype, B, False, 0, 0.0, 0, pt, gptrs, saved, work)
+        check(L.mmoe_img_proj_bwd(C.byref(c), d, proj, do.data_ptr(), dx.data_ptr()), "img_proj_bwd")
+        grads = [v if req else None for v, req in zip(views, ctx.param_req)]
+        return (None, None, None, dx.to(ctx.in_dtype), *grads)

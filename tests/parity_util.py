@@ -1,0 +1,140 @@
+"""Shared helpers for the GPU parity tests: build a CUDA drop-in module for a case, run it,
+and compare with the CPU oracle (oracle/) and the committed golden vectors."""
+from __future__ import annotations
+
+import contextlib
+from collections import OrderedDict
+from typing import Dict, List, Optional
+
+import torch
+
+from oracle import cases as C
+
+# tolerances from BASELINE.json north_star: "logits and gradients within rtol 2e-2 for bf16 and 1e-4 for fp32".
+# The error measure is max|a-b| / max|ref| per tensor (a relative error against the tensor's scale; an
+# element-wise rtol is meaningless for entries that are ~0 by cancellation).
+TOL = {"fp32": 1e-4, "bf16": 2e-2, "fp16": 2e-2}
+
+
+class _Tokens:
+    def __init__(self, t):
+        self.last_hidden_state = t
+
+
+class FakeBackbone(torch.nn.Module):
+    """Stand-in for the HF ViT (not part of the re-implemented path): returns its input as tokens."""
+
+    class _Cfg:
+        hidden_size = 768
+
+    config = _Cfg()
+
+    def forward(self, pixel_values):
+        return _Tokens(pixel_values)
+
+
+def build_module(case: C.Case, device="cuda"):
+    import mmoe_multimodal_rec_b200 as pkg
+    M, H = pkg.modules, pkg.modules_home
+    k = case.kind
+    if k == "head":
+        m = M.TwoTaskMMoE(**case.ctor)
+    elif k == "home_head":
+        m = H.HOME_MMoE_Complete(expert_dim=768, **case.ctor)
+    elif k == "cross":
+        m = M.RobustTextCrossExpert()
+    elif k == "cross_home":
+        m = H.RobustTextCrossExpert()
+    elif k == "fuse":
+        m = M.EnhancedCrossFuse()
+    elif k == "fuse_home":
+        m = H.EnhancedCrossFuse()
+    elif k == "img_pool":
+        m = M.ItemImageExpert(FakeBackbone(), pool_type=case.ctor.get("pool_type", "mean"))
+    elif k == "img_proj":
+        m = H.ImageExpertWithProjection(FakeBackbone())
+    else:
+        raise KeyError(k)
+    m.load_state_dict(case.state_dict(), strict=True)
+    return m.to(device).eval()
+
+
+def autocast_ctx(mode: str):
+    if mode == "fp32":
+        return contextlib.nullcontext()
+    return torch.autocast("cuda", dtype=torch.bfloat16 if mode == "bf16" else torch.float16)
+
+
+def run_cuda(case: C.Case, mode: str = "fp32", module=None):
+    """Forward + backward of the CUDA drop-in. Returns (outs, input_grads, param_grads) on CPU (fp32)."""
+    mod = module if module is not None else build_module(case)
+    mod.zero_grad(set_to_none=True)
+    raw = case.inputs()
+    meta = case.inputs_meta()
+    ins = [t.cuda().clone().requires_grad_(True) if f else t.cuda() for t, f in zip(raw, meta)]
+    with autocast_ctx(mode):
+        if case.kind == "img_pool":
+            out = mod(ins[0], trainable=True)
+        elif case.kind == "img_proj":
+            out = mod(ins[0])[1]
+        else:
+            out = mod(*ins)
+    outs = tuple(out) if isinstance(out, (tuple, list)) else (out,)
+    cots = case.cotangents([o.detach().cpu() for o in outs])
+    torch.autograd.backward(list(outs), [c.to(o.device, o.dtype) for c, o in zip(cots, outs)])
+    torch.cuda.synchronize()
+    gin = [t.grad.detach().float().cpu() if f else None for t, f in zip(ins, meta)]
+    gp = OrderedDict((n, (p.grad.detach().float().cpu() if p.grad is not None else None))
+                     for n, p in mod.named_parameters() if not n.startswith("backbone") and not n.startswith("vit_model"))
+    return [o.detach().float().cpu() for o in outs], gin, gp
+
+
+def nerr(a: torch.Tensor, ref: torch.Tensor) -> float:
+    a, ref = a.double(), ref.double()
+    if not torch.isfinite(a).all():
+        return float("inf")
+    return float((a - ref).abs().max()) / max(float(ref.abs().max()), 1e-30)
+
+
+def compare_with_oracle(case: C.Case, mode: str, module=None) -> Dict[str, float]:
+    """Normalised errors of every output / gradient of the CUDA path against the float64 oracle."""
+    o_out, o_gin, o_gp = C.run_oracle(case, torch.float64)
+    c_out, c_gin, c_gp = run_cuda(case, mode, module)
+    errs: Dict[str, float] = {}
+    for j, (a, b) in enumerate(zip(c_out, o_out)):
+        errs[f"out{j}"] = nerr(a, b)
+    for j, (a, b) in enumerate(zip(c_gin, o_gin)):
+        if b is not None:
+            errs[f"grad_in{j}"] = nerr(a, b)
+    used = set(case.used_param_keys())
+    for k, ref in o_gp.items():
+        if k in used:
+            errs["d_" + k] = nerr(c_gp[k], ref) if c_gp.get(k) is not None else float("inf")
+        else:
+            errs["unused_" + k] = 0.0 if c_gp.get(k) is None else float("inf")
+    return errs
+
+
+def check_against_golden(case: C.Case, golden: dict, mode: str, module=None) -> Dict[str, float]:
+    """The CUDA path against what the real reference computed (tests/golden/<case>.pt)."""
+    c_out, c_gin, c_gp = run_cuda(case, mode, module)
+    errs: Dict[str, float] = {}
+    for j, (a, b) in enumerate(zip(c_out, golden["out"])):
+        errs[f"out{j}"] = nerr(a, b)
+    tol = TOL[mode]
+    for j, (a, fp) in enumerate(zip(c_gin, golden["grad_in"])):
+        if fp is not None:
+            try:
+                C.check_fingerprint(a, fp, tol, f"{case.name} grad_in{j}")
+                errs[f"grad_in{j}"] = 0.0
+            except AssertionError as e:
+                errs[f"grad_in{j}:{e}"] = float("inf")
+    for k, fp in golden["grad_param"].items():
+        if fp is None:
+            continue
+        try:
+            C.check_fingerprint(c_gp[k], fp, tol, f"{case.name} d_{k}")
+            errs["d_" + k] = 0.0
+        except AssertionError as e:
+            errs[f"d_{k}:{e}"] = float("inf")
+    return errs
