@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native MMoE fusion-and-head path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]; SURVEY.md §8d "v1 fusion path"): one fwd+bwd pass of the v1 fusion-and-head
+path of the reference's train.py micro-step (train.py:244-254) under bf16 autocast on a batch of B=512 samples
+per GPU: ItemImageExpert tail (token mean + LN + dropout) -> RobustTextCrossExpert -> 2x EnhancedCrossFuse ->
+stack -> TwoTaskMMoE -> 2x BCEWithLogits -> backward.  Modules are in train() mode (dropout 0.1 active, as in
+training).  Synthetic inputs of the shapes the encoders produce (sentence vectors [B,64,768] + masks, doc
+vectors, ViT tokens [B,197,768]) and random-init weights; the text encoders / ViT backbone are the reference's
+own torch modules and are not part of the timed path (north_star: "timed separately").
+For N > 1 each rank runs the same per-GPU batch (weak scaling) and the gradients of the four trainable modules
+are all-reduced by DistributedDataParallel over NCCL, overlapped with backward.
+
+One JSON line on stdout (rank 0); see README / DESIGN.md for the keys.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "mmoe_fusion_head_fwd_bwd_samples_per_sec"
+UNIT = "samples/s"
+S, D, NTOK = 64, 768, 197
+# algorithmic GEMM FLOPs of the v1 fusion path per sample, fwd+bwd (SURVEY.md §8d / BASELINE.md §3)
+FLOP_PER_SAMPLE = 12.366e9
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic inputs (oracle/synth.py is test infrastructure; the bench makes its own with torch RNG)
+# ----------------------------------------------------------------------------------------------
+def make_host_batch(B: int, seed: int, pin: bool):
+    g = torch.Generator().manual_seed(seed)
+    def t(*shape):
+        x = torch.randn(*shape, generator=g)
+        return x.pin_memory() if pin else x
+    lens_u = torch.randint(1, S + 1, (B,), generator=g)
+    lens_i = torch.randint(1, S + 1, (B,), generator=g)
+    ar = torch.arange(S)[None]
+    batch = {
+        "u_sent": t(B, S, D), "i_sent": t(B, S, D),
+        "u_mask": (ar >= lens_u[:, None]), "i_mask": (ar >= lens_i[:, None]),
+        "u_doc": t(B, D), "i_doc": t(B, D), "img_tokens": t(B, NTOK, D),
+        "y_good": (torch.rand(B, generator=g) < 0.5).float(), "y_best": (torch.rand(B, generator=g) < 0.5).float(),
+    }
+    if pin:
+        for k in ("u_mask", "i_mask", "y_good", "y_best"):
+            batch[k] = batch[k].pin_memory()
+    return batch
+
+
+def h2d_bytes(batch) -> int:
+    return sum(v.numel() * v.element_size() for v in batch.values())
+
+
+class Passthrough(torch.nn.Module):
+    """Stands in for the HF ViT backbone (excluded from the timed path): hands the given tokens on."""
+    class _Cfg:
+        hidden_size = D
+    config = _Cfg()
+
+    def forward(self, pixel_values):
+        class _O:
+            pass
+        o = _O()
+        o.last_hidden_state = pixel_values
+        return o
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            try:
+                sm.append(float(parts[0])); mx = max(mx, float(parts[1]))
+                for n, v in zip(names, parts[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's modules on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_oracle_step_fn(B: int):
+    """fwd+bwd of the same path through oracle/ (CPU restatement of the reference) in fp32, eval-mode arithmetic
+    (the oracle has no RNG; dropout costs the reference extra time on CPU, so this favours the baseline)."""
+    from oracle import mmoe_oracle as O
+    from oracle import synth
+    torch.manual_seed(0)
+    sds = {
+        "img": synth.fill_state_dict(synth.image_wrapper_shapes(), 1),
+        "cross": synth.fill_state_dict(synth.cross_expert_shapes(), 2),
+        "concat_ui": synth.fill_state_dict(synth.cross_fuse_shapes(), 3),
+        "concat_ti": synth.fill_state_dict(synth.cross_fuse_shapes(), 4),
+        "head": synth.fill_state_dict(synth.mmoe_head_shapes(), 5),
+    }
+    for sd in sds.values():
+        for v in sd.values():
+            v.requires_grad_(True)
+    b = make_host_batch(B, 99, pin=False)
+    for k in ("u_sent", "i_sent", "u_doc", "i_doc"):
+        b[k].requires_grad_(True)
+
+    def step():
+        for sd in sds.values():
+            for v in sd.values():
+                v.grad = None
+        lg, lb = O.v1_fusion_path(sds, b["u_sent"], b["u_mask"], b["i_sent"], b["i_mask"], b["u_doc"], b["i_doc"], b["img_tokens"])
+        loss = O.bce_with_logits(lg, b["y_good"], O.POS_WEIGHT_GOOD) + O.bce_with_logits(lb, b["y_best"], O.POS_WEIGHT_BEST)
+        loss.backward()
+        return float(loss)
+    return step
+
+
+def time_cpu_oracle(B: int, steps: int, warmup: int):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_oracle_step_fn(B)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return B / dt, dt * 1e3, cores
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    B = args.ref_batch
+    value, ms, cores = time_cpu_oracle(B, max(args.steps, 1), max(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.batch, args.gpus) | {"sample": f"{B} samples per step on the host CPU"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"oracle/ port of the reference modules, fp32, {B}-sample batch, fwd+bwd, {args.steps} steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(B, n_gpus):
+    return {"workload": "v1 MMoE fusion-and-head path fwd+bwd (ItemImageExpert tail + RobustTextCrossExpert + 2x EnhancedCrossFuse "
+                        "+ TwoTaskMMoE + BCE), train mode, BASELINE configs[1]",
+            "per_gpu_batch": B, "global_batch": B * n_gpus, "sentences": S, "d_model": D, "parallelism": f"dp{n_gpus}",
+            "autocast": "bf16", "l2": "inputs (~0.5 GB/step) and activations (~3 GB) exceed the 126 MB L2; no flush needed",
+            "encoders": "text encoders / ViT backbone excluded (reference torch modules, timed separately)"}
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=512, help="per-GPU batch (train.py default 512)")
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--ref-batch", type=int, default=16, help="samples per step of the CPU reference arm")
+    ap.add_argument("--cpu-baseline-batch", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eval-mode", action="store_true", help="dropout off (debug)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    import mmoe_multimodal_rec_b200 as pkg
+    from mmoe_multimodal_rec_b200._lib import check
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = pkg.lib()
+    check(L.mmoe_init(), "init")
+
+    M = pkg.modules
+    torch.manual_seed(1234)
+    img = M.ItemImageExpert(Passthrough(), pool_type="mean").to(dev)
+    cross = M.RobustTextCrossExpert().to(dev)
+    cui = M.EnhancedCrossFuse().to(dev)
+    cti = M.EnhancedCrossFuse().to(dev)
+    head = M.TwoTaskMMoE().to(dev)
+    mods = [img, cross, cui, cti, head]
+    for m in mods:
+        m.train(not args.eval_mode)
+    if distributed:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        cross_c, cui_c, cti_c, head_c = (DDP(m, device_ids=[local_rank]) for m in (cross, cui, cti, head))
+    else:
+        cross_c, cui_c, cti_c, head_c = cross, cui, cti, head
+    pw_g = torch.tensor(858627.0 / 990303.0, device=dev)      # train.py:189-192
+    pw_b = torch.tensor(1328721.0 / 520209.0, device=dev)
+
+    B = args.batch
+    n_host = 2
+    host = [make_host_batch(B, 1234 + rank * 17 + j, pin=True) for j in range(n_host)]
+    resident = {k: v.to(dev) for k, v in host[0].items()}
+    grad_keys = ("u_sent", "i_sent", "u_doc", "i_doc")
+
+    def step(b):
+        for m in mods:
+            m.zero_grad(set_to_none=True)
+        ins = {k: (v.detach().requires_grad_(True) if k in grad_keys else v) for k, v in b.items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            img_vec = img(ins["img_tokens"], trainable=False)
+            ui = cross_c(ins["u_sent"], ins["u_mask"], ins["i_sent"], ins["i_mask"])
+            xui = cui_c(ins["u_doc"], img_vec)
+            xti = cti_c(ins["i_doc"], img_vec)
+            ev = torch.stack([ins["u_doc"], ins["i_doc"], img_vec, ui, xui, xti], dim=1)
+            lg, lb = head_c(ev)
+            loss = F.binary_cross_entropy_with_logits(lg.float(), ins["y_good"], pos_weight=pw_g) + \
+                   F.binary_cross_entropy_with_logits(lb.float(), ins["y_best"], pos_weight=pw_b)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing ----------------
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    barrier()
+    L.mmoe_launch_count(1)
+    L.mmoe_gemm_timing(1)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        loss = step(resident)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    L.mmoe_gemm_timing(0)
+    ms_total = ev0.elapsed_time(ev1)
+    launches = int(L.mmoe_launch_count(1))
+    g_ms, g_fl, g_n = C.c_double(), C.c_double(), C.c_int64()
+    L.mmoe_gemm_timing_read(C.byref(g_ms), C.byref(g_fl), C.byref(g_n), 1)
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = B * world / (ms_step * 1e-3)
+
+    # ---------------- end-to-end timing: pinned host -> device every step, loss read back ----------------
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [None, None]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    done = [torch.cuda.Event(), torch.cuda.Event()]      # compute finished with the slot
+
+    def prefetch(j, src):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done[j])
+            slots[j] = {k: v.to(dev, non_blocking=True) for k, v in src.items()}
+            ready[j].record(copy_stream)
+
+    cur = torch.cuda.current_stream()
+    for j in range(2):
+        done[j].record(cur)
+
+    def e2e_loop(n):
+        prefetch(0, host[0])
+        last = None
+        for i in range(n):
+            j = i & 1
+            if i + 1 < n:
+                prefetch(j ^ 1, host[(i + 1) % n_host])
+            cur.wait_event(ready[j])
+            for v in slots[j].values():
+                v.record_stream(cur)
+            l = step(slots[j])
+            done[j].record(cur)
+            last = float(l.item())          # device -> host read of the step's result
+        return last
+
+    e2e_loop(3)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    e2e_loop(args.steps)
+    ev1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e_ms = max(ev0.elapsed_time(ev1), 0.0)
+    t = torch.tensor([e_ms], device=dev, dtype=torch.float64)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = B * world / (float(t.item()) / args.steps * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS, measured)" if peaks else "fallback 1400 TFLOP/s sustained (B200_PROFILING.md)"
+        achieved = (g_fl.value / (g_ms.value * 1e-3)) / 1e12 if g_ms.value > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": workload_config(B, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(host[0]), "d2h_bytes_per_step": 4,
+                    "note": "pinned host batch copied on a side stream (double buffered) every step; loss.item() read back every step"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 grouped GEMM, all launches of the timed region)",
+                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
+                         "traffic": None, "peak_source": peak_src,
+                         "gemm_ms_per_step": g_ms.value / args.steps, "gemm_launches_per_step": g_n.value / args.steps,
+                         "gemm_share_of_step": (g_ms.value / args.steps) / ms_step if ms_step else None,
+                         "path_tflops": FLOP_PER_SAMPLE * B / (ms_step * 1e-3) / 1e12,
+                         "path_frac_of_peak": FLOP_PER_SAMPLE * B / (ms_step * 1e-3) / 1e12 / peak_tf},
+            "loss": float(loss.item()),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                v, ms_cpu, cores = time_cpu_oracle(args.cpu_baseline_batch, 2, 1)
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                        "sample": f"oracle/ port of the reference modules, fp32, {args.cpu_baseline_batch}-sample batch, "
+                                                  f"fwd+bwd, 2 timed steps ({ms_cpu:.0f} ms/step)"}
+            except Exception as ex:  # noqa: BLE001
+                line["cpu_baseline"] = {"error": repr(ex)}
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -101,6 +101,12 @@ typedef struct {
 int mmoe_gemm_grouped(const mmoe_gemm_problem* problems /*host*/, int n_problems, int dtype,
                       int engine, void* stream);
 
+/* Live timing of the GEMM launches (bench.py's roofline): while enabled, CUDA events are recorded on the launching
+ * stream around every mmoe_gemm_grouped launch (also those issued by the module entry points).  _read sums the
+ * durations / algorithmic FLOPs (2*M*N*K) recorded since the last read — call it after a device synchronize. */
+int mmoe_gemm_timing(int enable);
+int mmoe_gemm_timing_read(double* total_ms, double* total_flops, int64_t* launches, int tc_only);
+
 /* keep-mask a kernel would use for flat element index i in [0,n): out[i] = 1/0 (uint8). */
 int mmoe_dropout_mask(uint32_t key0, uint32_t key1, float p, int64_t n, uint8_t* out, void* stream);
 
@@ -179,6 +185,11 @@ int mmoe_cross_fwd(const mmoe_call* c, const mmoe_cross_cfg* cfg, const float* u
 int mmoe_cross_bwd(const mmoe_call* c, const mmoe_cross_cfg* cfg, const float* user, const uint8_t* user_mask,
                    const float* item, const uint8_t* item_mask, const float* dout, float* d_user, float* d_item);
 
+/* Layout query for tests/debugging: byte range inside the saved blob of an encoder layer's activation.
+ * stream_id 0 = user stack, 1 = item stack; which 0 = FFN activation h [B*S,4d] T, 1 = layer output [B*S,d] fp32. */
+int mmoe_cross_saved_offset(const mmoe_cross_cfg* cfg, int32_t B, int dtype, int home, int stream_id, int layer, int which,
+                            size_t* offset, size_t* bytes);
+
 /* EnhancedCrossFuse.forward — model.py:491-507; home=1: model_HoME.py:506-522 (returns
  * fused + identity).  v_cls,t_cls fp32 [B,d]; out fp32 [B,d]. */
 typedef struct { int32_t d, n_head, depth; } mmoe_fuse_cfg;
@@ -187,6 +198,9 @@ size_t mmoe_fuse_workspace_bytes(const mmoe_fuse_cfg* cfg, int32_t B, int dtype)
 int mmoe_fuse_fwd(const mmoe_call* c, const mmoe_fuse_cfg* cfg, const float* v_cls, const float* t_cls, float* out);
 /* d_cat fp32 [B,2,d]: d_cat[:,0,:] is the gradient of v_cls, d_cat[:,1,:] of t_cls. */
 int mmoe_fuse_bwd(const mmoe_call* c, const mmoe_fuse_cfg* cfg, const float* dout, float* d_cat);
+
+int mmoe_fuse_saved_offset(const mmoe_fuse_cfg* cfg, int32_t B, int dtype, int home, int layer, int which,
+                           size_t* offset, size_t* bytes);
 
 /* HOME_MMoE_Complete.forward — model_HoME.py:590-638 (ExpertMLP 28-35, FeatureGate 232-234,
  * SelfGate 242-243, DenseGate 251-252, tower 581-588).  expert_vecs fp32 [B,n_in,d];

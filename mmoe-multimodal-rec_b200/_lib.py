@@ -77,6 +77,8 @@ PROTOTYPES = {
     "mmoe_launch_count": (_i64, [C.c_int]),
     "mmoe_cast_f32": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp]),
     "mmoe_gemm_grouped": (C.c_int, [_P(GemmProblem), C.c_int, C.c_int, C.c_int, _vp]),
+    "mmoe_gemm_timing": (C.c_int, [C.c_int]),
+    "mmoe_gemm_timing_read": (C.c_int, [_P(C.c_double), _P(C.c_double), _P(_i64), C.c_int]),
     "mmoe_dropout_mask": (C.c_int, [_u32, _u32, _f, _i64, _vp, _vp]),
     "mmoe_layernorm_fwd": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _i64, _i32, C.c_int, _vp]),
     "mmoe_attention_fwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32,
@@ -93,6 +95,8 @@ PROTOTYPES = {
     "mmoe_cross_workspace_bytes": (_sz, [_P(CrossCfg), _i32, C.c_int]),
     "mmoe_cross_fwd": (C.c_int, [_P(Call), _P(CrossCfg), _vp, _vp, _vp, _vp, _vp]),
     "mmoe_cross_bwd": (C.c_int, [_P(Call), _P(CrossCfg), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mmoe_cross_saved_offset": (C.c_int, [_P(CrossCfg), _i32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P(_sz), _P(_sz)]),
+    "mmoe_fuse_saved_offset": (C.c_int, [_P(FuseCfg), _i32, C.c_int, C.c_int, C.c_int, C.c_int, _P(_sz), _P(_sz)]),
     "mmoe_fuse_saved_bytes": (_sz, [_P(FuseCfg), _i32, C.c_int]),
     "mmoe_fuse_workspace_bytes": (_sz, [_P(FuseCfg), _i32, C.c_int]),
     "mmoe_fuse_fwd": (C.c_int, [_P(Call), _P(FuseCfg), _vp, _vp, _vp]),

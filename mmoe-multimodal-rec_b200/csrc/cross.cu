@@ -219,6 +219,23 @@ extern "C" size_t mmoe_cross_saved_bytes(const mmoe_cross_cfg* cfg, int32_t B, i
   cross_layout(A, *cfg, B, dtype, 0);
   return A.off + 256;
 }
+// layout query (tests / debugging): byte range of a saved activation inside the blob.
+// stream_id 0 = user stack, 1 = item stack; which: 0 = h (post ReLU/dropout FFN activation [B*S, 4d] T),
+// 1 = x2 (layer output, fp32 [B*S, d]).
+extern "C" int mmoe_cross_saved_offset(const mmoe_cross_cfg* cfg, int32_t B, int dtype, int home, int stream_id, int layer, int which,
+                                       size_t* offset, size_t* bytes) {
+  MMOE_TRY(check_cfg(cfg, B));
+  MMOE_CHECK(layer >= 0 && layer < cfg->n_layer && (stream_id == 0 || stream_id == 1), "saved_offset: bad layer/stream");
+  Arena A(nullptr);
+  CrossSaved s = cross_layout(A, *cfg, B, dtype, home);
+  const EncSaved& e = stream_id == 0 ? s.user[layer] : s.item[layer];
+  const size_t M = (size_t)B * cfg->S;
+  if (which == 0) { *offset = (size_t)(char*)e.h; *bytes = M * 4 * cfg->d * dtype_size(dtype); }
+  else if (which == 1) { *offset = (size_t)(char*)e.x2; *bytes = M * cfg->d * 4; }
+  else { set_error("saved_offset: unknown buffer %d", which); return -1; }
+  return 0;
+}
+
 extern "C" size_t mmoe_cross_workspace_bytes(const mmoe_cross_cfg* cfg, int32_t B, int dtype) {
   Arena A(nullptr);
   cross_scratch_layout(A, *cfg, B, dtype);

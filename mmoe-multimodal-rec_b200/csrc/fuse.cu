@@ -282,6 +282,18 @@ extern "C" size_t mmoe_fuse_saved_bytes(const mmoe_fuse_cfg* cfg, int32_t B, int
   fuse_layout(A, *cfg, B, dtype, 0);
   return A.off + 256;
 }
+// layout query (tests / debugging), see mmoe_cross_saved_offset.  which: 0 = h of encoder layer `layer` ([2B, 4d] T)
+extern "C" int mmoe_fuse_saved_offset(const mmoe_fuse_cfg* cfg, int32_t B, int dtype, int home, int layer, int which,
+                                      size_t* offset, size_t* bytes) {
+  MMOE_TRY(check_fuse(cfg));
+  MMOE_CHECK(layer >= 0 && layer < cfg->depth && which == 0, "saved_offset: bad layer/buffer");
+  Arena A(nullptr);
+  FuseSaved s = fuse_layout(A, *cfg, B, dtype, home);
+  *offset = (size_t)(char*)s.layer[layer].h;
+  *bytes = (size_t)2 * B * 4 * cfg->d * dtype_size(dtype);
+  return 0;
+}
+
 extern "C" size_t mmoe_fuse_workspace_bytes(const mmoe_fuse_cfg* cfg, int32_t B, int dtype) {
   Arena A(nullptr);
   fuse_scratch_layout(A, *cfg, B, dtype);

@@ -14,7 +14,10 @@
 // transpose bits), so forward, dgrad and wgrad need no transposed copies.
 #include <cuda.h>
 
+#include <atomic>
 #include <cstdlib>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -566,7 +569,44 @@ static int launch_simt(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// live timing of the GEMM launches (bench.py's roofline): CUDA events recorded on the launching stream around
+// every grouped launch while enabled; read back after a synchronize.
+// ------------------------------------------------------------------------------------------
+struct TimedLaunch { cudaEvent_t a, b; double flops; int tc; };
+static std::mutex g_time_mu;
+static std::vector<TimedLaunch> g_timed;
+static std::vector<cudaEvent_t> g_event_pool;
+static std::atomic<int> g_timing_on{0};
+
+static cudaEvent_t take_event() {
+  cudaEvent_t e;
+  if (!g_event_pool.empty()) { e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEventCreate(&e);
+  return e;
+}
+
+static int gemm_grouped_untimed(const mmoe_gemm_problem* problems, int n_problems, int dtype, int engine, cudaStream_t stream);
+
 int gemm_grouped(const mmoe_gemm_problem* problems, int n_problems, int dtype, int engine, cudaStream_t stream) {
+  if (!g_timing_on.load(std::memory_order_relaxed)) return gemm_grouped_untimed(problems, n_problems, dtype, engine, stream);
+  TimedLaunch t;
+  t.flops = 0.0;
+  for (int i = 0; i < n_problems; ++i) t.flops += 2.0 * problems[i].M * (double)problems[i].N * problems[i].K;
+  t.tc = (dtype != MMOE_F32 && engine != 1) ? 1 : 0;
+  {
+    std::lock_guard<std::mutex> lk(g_time_mu);
+    t.a = take_event(); t.b = take_event();
+  }
+  cudaEventRecord(t.a, stream);
+  const int rc = gemm_grouped_untimed(problems, n_problems, dtype, engine, stream);
+  cudaEventRecord(t.b, stream);
+  std::lock_guard<std::mutex> lk(g_time_mu);
+  g_timed.push_back(t);
+  return rc;
+}
+
+static int gemm_grouped_untimed(const mmoe_gemm_problem* problems, int n_problems, int dtype, int engine, cudaStream_t stream) {
   MMOE_CHECK(n_problems >= 1 && n_problems <= kMaxGroups, "n_problems must be in [1,%d]", kMaxGroups);
   for (int i = 0; i < n_problems; ++i) {
     const mmoe_gemm_problem& q = problems[i];
@@ -586,4 +626,25 @@ int gemm_grouped(const mmoe_gemm_problem* problems, int n_problems, int dtype, i
 
 extern "C" int mmoe_gemm_grouped(const mmoe_gemm_problem* problems, int n_problems, int dtype, int engine, void* stream) {
   return mmoe::gemm_grouped(problems, n_problems, dtype, engine, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mmoe_gemm_timing(int enable) {
+  mmoe::g_timing_on.store(enable ? 1 : 0);
+  return 0;
+}
+// Sums over the launches recorded since the last read (call after a device synchronize); clears the record.
+extern "C" int mmoe_gemm_timing_read(double* total_ms, double* total_flops, int64_t* launches, int tc_only) {
+  using namespace mmoe;
+  std::lock_guard<std::mutex> lk(g_time_mu);
+  double ms = 0.0, fl = 0.0;
+  int64_t n = 0;
+  for (auto& t : g_timed) {
+    float dt = 0.f;
+    if (cudaEventElapsedTime(&dt, t.a, t.b) == cudaSuccess && (!tc_only || t.tc)) { ms += dt; fl += t.flops; ++n; }
+    g_event_pool.push_back(t.a);
+    g_event_pool.push_back(t.b);
+  }
+  g_timed.clear();
+  *total_ms = ms; *total_flops = fl; *launches = n;
+  return 0;
 }

@@ -1,12 +1,15 @@
 // Bandwidth-bound helper kernels: casts, dropout masks, LayerNorm forward/backward.
 // All rows are d <= 1024 wide (d = 768 on this path), d % 4 == 0; one warp owns a row and
 // moves it with 128-bit (fp32) / 64-bit (16-bit types) coalesced accesses.
+#include <atomic>
+
 #include "kernels.cuh"
 
 namespace mmoe {
 
 thread_local char g_error[512] = {0};
-thread_local int64_t g_launches = 0;
+// process-wide: forward runs on the Python thread, backward on the autograd worker thread
+static std::atomic<int64_t> g_launches{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -14,7 +17,7 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_error, sizeof(g_error), fmt, ap);
   va_end(ap);
 }
-void count_launch(int n) { g_launches += n; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ---------------------------------------------------------------- vector load/store helpers
 template <typename T> __device__ __forceinline__ float4 load4(const T* p);
@@ -356,8 +359,8 @@ extern "C" size_t mmoe_abi_sizeof(int which) {
 }
 extern "C" const char* mmoe_last_error(void) { return mmoe::g_error; }
 extern "C" int64_t mmoe_launch_count(int reset) {
-  const int64_t n = mmoe::g_launches;
-  if (reset) mmoe::g_launches = 0;
+  const int64_t n = mmoe::g_launches.load();
+  if (reset) mmoe::g_launches.store(0);
   return n;
 }
 extern "C" int mmoe_init(void) {

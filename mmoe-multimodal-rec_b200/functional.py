@@ -15,6 +15,9 @@ from torch.autograd.function import once_differentiable
 from . import _lib
 from ._lib import BF16, F16, F32, Call, CrossCfg, FuseCfg, HeadCfg, HomeCfg, check, lib, ptr_array
 
+# test hook: when set to a list, CrossFn / FuseFn append (kind, cfg, home, B, dtype, saved_blob) after forward
+DEBUG_SAVED = None
+
 _TORCH2MMOE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 _MMOE2TORCH = {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}
 
@@ -204,6 +207,8 @@ class CrossFn(torch.autograd.Function):
         seed = _new_seed(training, drop_p)
         c = _call(dtype, B, training, home, drop_p, seed, pt, None, saved, None)
         check(L.mmoe_cross_fwd(C.byref(c), C.byref(cfg), u.data_ptr(), um.data_ptr(), it.data_ptr(), im.data_ptr(), out.data_ptr()), "cross_fwd")
+        if DEBUG_SAVED is not None:
+            DEBUG_SAVED.append(("cross", cfg, home, B, dtype, saved))
         ctx.state = (cfg, home, list(used), training, drop_p, seed, dtype, u, um, it, im, pt, saved)
         ctx.param_req = [p.requires_grad for p in params]
         ctx.in_dtypes = (user.dtype, item.dtype)
@@ -246,6 +251,8 @@ class FuseFn(torch.autograd.Function):
         seed = _new_seed(training, drop_p)
         c = _call(dtype, B, training, home, drop_p, seed, pt, None, saved, None)
         check(L.mmoe_fuse_fwd(C.byref(c), C.byref(cfg), v.data_ptr(), t.data_ptr(), out.data_ptr()), "fuse_fwd")
+        if DEBUG_SAVED is not None:
+            DEBUG_SAVED.append(("fuse", cfg, home, B, dtype, saved))
         ctx.state = (cfg, home, list(used), training, drop_p, seed, dtype, B, dev, pt, saved)
         ctx.param_req = [p.requires_grad for p in params]
         ctx.in_dtypes = (v_cls.dtype, t_cls.dtype)

@@ -78,21 +78,22 @@ class Case:
         return [True]
 
     # ---- oracle forward -------------------------------------------------
-    def oracle_forward(self, sd, inputs) -> Tuple[torch.Tensor, ...]:
+    def oracle_forward(self, sd, inputs, relu_masks=None, trace=None) -> Tuple[torch.Tensor, ...]:
         k = self.kind
+        kw = dict(relu_masks=relu_masks, trace=trace)
         if k == "head":
             return tuple(O.two_task_mmoe(sd, *inputs))
         if k == "home_head":
             return tuple(O.home_mmoe(sd, *inputs, n_shared=self.ctor.get("n_shared_experts", 4),
                                      n_task=self.ctor.get("n_task_experts", 2)))
         if k == "cross":
-            return (O.cross_expert(sd, *inputs),)
+            return (O.cross_expert(sd, *inputs, **kw),)
         if k == "cross_home":
-            return (O.cross_expert(sd, *inputs, home=True),)
+            return (O.cross_expert(sd, *inputs, home=True, **kw),)
         if k == "fuse":
-            return (O.cross_fuse(sd, *inputs),)
+            return (O.cross_fuse(sd, *inputs, **kw),)
         if k == "fuse_home":
-            return (O.cross_fuse(sd, *inputs, home=True),)
+            return (O.cross_fuse(sd, *inputs, home=True, **kw),)
         if k == "img_pool":
             return (O.item_image_pool(sd, *inputs, pool_type=self.ctor.get("pool_type", "mean")),)
         if k == "img_proj":
@@ -114,13 +115,14 @@ class Case:
         return keys
 
 
-def run_oracle(case: Case, dtype=torch.float64):
-    """Forward + backward of the oracle.  Returns (outs, input_grads, param_grads)."""
+def run_oracle(case: Case, dtype=torch.float64, relu_masks=None, trace=None):
+    """Forward + backward of the oracle.  Returns (outs, input_grads, param_grads).
+    ``relu_masks`` / ``trace``: see mmoe_oracle.encoder_layer (activation-pattern injection for low-precision parity)."""
     sd = OrderedDict((k, v.to(dtype).clone().requires_grad_(True)) for k, v in case.state_dict().items())
     raw = case.inputs()
     meta = case.inputs_meta()
     ins = [t.to(dtype).clone().requires_grad_(True) if f else t for t, f in zip(raw, meta)]
-    outs = case.oracle_forward(sd, ins)
+    outs = case.oracle_forward(sd, ins, relu_masks, trace)
     cots = case.cotangents(outs)
     torch.autograd.backward(list(outs), [c.to(dtype) for c in cots])
     gin = [t.grad if f else None for t, f in zip(ins, meta)]

@@ -108,7 +108,7 @@ def multi_head_attention(sd: Mapping[str, Tensor], prefix: str, q_in: Tensor, kv
 
 
 def encoder_layer(sd: Mapping[str, Tensor], prefix: str, x: Tensor, key_padding_mask: Optional[Tensor],
-                  n_head: int, drop: Drop = None) -> Tensor:
+                  n_head: int, drop: Drop = None, relu_masks=None, trace=None) -> Tensor:
     """Pre-LN encoder layer, ReLU feed-forward.
 
     model.py:207-212 (RobustTransformerLayer) and the stock
@@ -120,7 +120,14 @@ def encoder_layer(sd: Mapping[str, Tensor], prefix: str, x: Tensor, key_padding_
                               drop, prefix + "self_attn")
     x = x + _drop(drop, prefix + "dropout1", sa)
     h = layer_norm(x, sd[prefix + "norm2.weight"], sd[prefix + "norm2.bias"])
-    f = torch.relu(linear(h, sd[prefix + "linear1.weight"], sd[prefix + "linear1.bias"]))
+    z = linear(h, sd[prefix + "linear1.weight"], sd[prefix + "linear1.bias"])
+    if trace is not None:
+        trace[prefix + "ffn_pre"] = z.detach()
+    if relu_masks is not None and (prefix + "relu") in relu_masks:
+        # test hook: use a given activation pattern (e.g. the one a low-precision kernel produced) instead of z > 0
+        f = z * relu_masks[prefix + "relu"].to(z.dtype).reshape(z.shape)
+    else:
+        f = torch.relu(z)
     f = _drop(drop, prefix + "dropout", f)
     f = linear(f, sd[prefix + "linear2.weight"], sd[prefix + "linear2.bias"])
     return x + _drop(drop, prefix + "dropout2", f)
@@ -146,13 +153,13 @@ def attn_pool(query: Tensor, x: Tensor, mask: Tensor, home: bool = False,
 # ----------------------------------------------------------------------------
 
 def cross_expert(sd: Mapping[str, Tensor], user: Tensor, user_mask: Tensor, item: Tensor, item_mask: Tensor,
-                 n_layer: int = 2, n_head: int = 8, home: bool = False, drop: Drop = None) -> Tensor:
+                 n_layer: int = 2, n_head: int = 8, home: bool = False, drop: Drop = None, relu_masks=None, trace=None) -> Tensor:
     """RobustTextCrossExpert.forward — model.py:426-451; HoME variant
     model_HoME.py:441-466 returns ``pooled`` (norm/mlp unused)."""
     for l in range(n_layer):
-        user = encoder_layer(sd, f"self_user.{l}.", user, user_mask, n_head, drop)
+        user = encoder_layer(sd, f"self_user.{l}.", user, user_mask, n_head, drop, relu_masks, trace)
     for l in range(n_layer):
-        item = encoder_layer(sd, f"self_item.{l}.", item, item_mask, n_head, drop)
+        item = encoder_layer(sd, f"self_item.{l}.", item, item_mask, n_head, drop, relu_masks, trace)
     cross = multi_head_attention(sd, "cross_attn.", user, item, item_mask, n_head, drop, "cross_attn")
     alpha = torch.sigmoid(sd["gate"])
     fused = alpha * user + (1.0 - alpha) * cross
@@ -167,7 +174,7 @@ def cross_expert(sd: Mapping[str, Tensor], user: Tensor, user_mask: Tensor, item
 
 
 def cross_fuse(sd: Mapping[str, Tensor], v_cls: Tensor, t_cls: Tensor, depth: int = 2, n_head: int = 8,
-               home: bool = False, drop: Drop = None) -> Tensor:
+               home: bool = False, drop: Drop = None, relu_masks=None, trace=None) -> Tensor:
     """EnhancedCrossFuse.forward — model.py:491-507; HoME variant
     model_HoME.py:506-522 returns ``fused + identity`` (proj unused)."""
     cat = torch.cat([v_cls, t_cls], dim=-1)
@@ -175,7 +182,7 @@ def cross_fuse(sd: Mapping[str, Tensor], v_cls: Tensor, t_cls: Tensor, depth: in
                           sd["res_proj.1.weight"], sd["res_proj.1.bias"])
     x = torch.stack([v_cls, t_cls], dim=1)                       # [B,2,d]
     for l in range(depth):
-        x = encoder_layer(sd, f"layers.{l}.", x, None, n_head, drop)
+        x = encoder_layer(sd, f"layers.{l}.", x, None, n_head, drop, relu_masks, trace)
     v_f, t_f = x[:, 0], x[:, 1]
     gi = torch.cat([v_f, t_f], dim=-1)
     g = torch.sigmoid(linear(gelu(linear(gi, sd["gate.0.weight"], sd["gate.0.bias"])),

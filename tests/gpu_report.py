@@ -161,9 +161,10 @@ def module_checks(report, quick):
             key = f"module/{case.name}/{mode}"
             t0 = time.time()
             try:
-                errs = PU.compare_with_oracle(case, mode)
+                stats = {}
+                errs = PU.compare_with_oracle(case, mode, stats=stats)
                 worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
-                report[key] = {"max": max(errs.values()), "worst": worst, "n": len(errs), "sec": round(time.time() - t0, 2)}
+                report[key] = {"max": max(errs.values()), "worst": worst, "n": len(errs), "sec": round(time.time() - t0, 2), **stats}
             except Exception as ex:  # noqa: BLE001
                 report[key] = {"error": repr(ex), "trace": traceback.format_exc()[-1500:]}
         try:

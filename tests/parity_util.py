@@ -96,10 +96,69 @@ def nerr(a: torch.Tensor, ref: torch.Tensor) -> float:
     return float((a - ref).abs().max()) / max(float(ref.abs().max()), 1e-30)
 
 
-def compare_with_oracle(case: C.Case, mode: str, module=None) -> Dict[str, float]:
-    """Normalised errors of every output / gradient of the CUDA path against the float64 oracle."""
-    o_out, o_gin, o_gp = C.run_oracle(case, torch.float64)
-    c_out, c_gin, c_gp = run_cuda(case, mode, module)
+def cuda_relu_masks(entries) -> Dict[str, torch.Tensor]:
+    """ReLU activation patterns (h != 0) the CUDA encoder layers produced, read out of the saved blob through
+    the library's layout query (mmoe_*_saved_offset)."""
+    import ctypes as Ct
+    import mmoe_multimodal_rec_b200 as pkg
+    from mmoe_multimodal_rec_b200._lib import check
+    L = pkg.lib()
+    tdt = {0: torch.float32, 1: torch.bfloat16, 2: torch.float16}
+    masks: Dict[str, torch.Tensor] = {}
+    for kind, cfg, home, B, dtype, blob in entries:
+        off, nbytes = Ct.c_size_t(), Ct.c_size_t()
+        if kind == "cross":
+            for sid, name in ((0, "self_user"), (1, "self_item")):
+                for l in range(cfg.n_layer):
+                    check(L.mmoe_cross_saved_offset(Ct.byref(cfg), B, dtype, int(home), sid, l, 0, Ct.byref(off), Ct.byref(nbytes)), "saved_offset")
+                    h = blob[off.value:off.value + nbytes.value].view(tdt[dtype]).reshape(-1, 4 * cfg.d)
+                    masks[f"{name}.{l}.relu"] = (h != 0).cpu()
+        else:
+            for l in range(cfg.depth):
+                check(L.mmoe_fuse_saved_offset(Ct.byref(cfg), B, dtype, int(home), l, 0, Ct.byref(off), Ct.byref(nbytes)), "saved_offset")
+                h = blob[off.value:off.value + nbytes.value].view(tdt[dtype]).reshape(-1, 4 * cfg.d)
+                masks[f"layers.{l}.relu"] = (h != 0).cpu()
+    return masks
+
+
+def compare_with_oracle(case: C.Case, mode: str, module=None, stats: Optional[dict] = None) -> Dict[str, float]:
+    """Normalised errors of every output / gradient of the CUDA path against the float64 oracle.
+
+    16-bit modes, modules with ReLU feed-forward layers: rounding the GEMM operands to 16 bits flips the sign of
+    the ~0.2 % of pre-activations that are within rounding noise of zero, and ReLU' is discontinuous there, so
+    *any* 16-bit evaluation (the reference's own autocast included) differs from fp64 by O(1) in isolated entries
+    of the linear1 gradients (measured: oracle/README note in DESIGN.md).  Gradients are therefore compared
+    against the oracle evaluated WITH THE ACTIVATION PATTERN THE KERNELS USED (read back from the saved blob),
+    and the pattern itself is checked separately: it may differ from the fp64 pattern only where |z| is within
+    rounding noise of zero (``stats['flip_frac']``, ``stats['flip_max_rel_z']``).
+    """
+    import mmoe_multimodal_rec_b200 as pkg
+    Fn = pkg.functional
+    inject = mode != "fp32" and case.kind in ("cross", "cross_home", "fuse", "fuse_home")
+    if inject:
+        Fn.DEBUG_SAVED = []
+    try:
+        c_out, c_gin, c_gp = run_cuda(case, mode, module)
+        entries = Fn.DEBUG_SAVED
+    finally:
+        Fn.DEBUG_SAVED = None
+    if inject:
+        masks = cuda_relu_masks(entries)
+        trace: Dict[str, torch.Tensor] = {}
+        o_out, o_gin, o_gp = C.run_oracle(case, torch.float64, relu_masks=masks, trace=trace)
+        flips, total, worst = 0, 0, 0.0
+        for key, m in masks.items():
+            z = trace[key.replace(".relu", ".ffn_pre")].reshape(m.shape)
+            diff = (z > 0) != m
+            flips += int(diff.sum())
+            total += m.numel()
+            if diff.any():
+                worst = max(worst, float(z[diff].abs().max() / z.std()))
+        if stats is not None:
+            stats["flip_frac"] = flips / max(total, 1)
+            stats["flip_max_rel_z"] = worst
+    else:
+        o_out, o_gin, o_gp = C.run_oracle(case, torch.float64)
     errs: Dict[str, float] = {}
     for j, (a, b) in enumerate(zip(c_out, o_out)):
         errs[f"out{j}"] = nerr(a, b)

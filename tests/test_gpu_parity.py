@@ -1,0 +1,156 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA drop-in modules, called through the C ABI, against the
+CPU oracle on the same deterministic weights/inputs, and against the golden vectors the real reference produced.
+
+Tolerances (BASELINE.json north_star): max|a-b|/max|ref| <= 1e-4 in fp32, <= 2e-2 under bf16 / fp16 autocast."""
+import pytest
+import torch
+
+import parity_util as PU
+from conftest import load_golden
+from oracle import cases as C
+
+pytestmark = pytest.mark.gpu
+IDS = [c.name for c in C.CASES]
+
+
+def _assert_ok(errs, tol, what):
+    bad = {k: v for k, v in errs.items() if not (v <= tol)}
+    assert not bad, f"{what}: {len(bad)} of {len(errs)} tensors above {tol}: {sorted(bad.items(), key=lambda kv: -kv[1])[:6]}"
+
+
+@pytest.mark.parametrize("case", C.CASES, ids=IDS)
+def test_fp32_matches_oracle(case):
+    _assert_ok(PU.compare_with_oracle(case, "fp32"), PU.TOL["fp32"], f"{case.name} fp32")
+
+
+@pytest.mark.parametrize("case", C.CASES, ids=IDS)
+def test_fp32_matches_reference_golden(case):
+    _assert_ok(PU.check_against_golden(case, load_golden(case.name), "fp32"), PU.TOL["fp32"], f"{case.name} golden")
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
+@pytest.mark.parametrize("case", C.CASES, ids=IDS)
+def test_16bit_autocast_matches_oracle(case, mode):
+    stats = {}
+    _assert_ok(PU.compare_with_oracle(case, mode, stats=stats), PU.TOL[mode], f"{case.name} {mode}")
+    if stats:
+        # the kernels' ReLU activation pattern may differ from the fp64 one only within rounding noise of zero
+        assert stats["flip_frac"] < 0.01 and stats["flip_max_rel_z"] < 0.05, stats
+
+
+def test_16bit_forward_matches_fp64_oracle_without_any_injection():
+    """Forward outputs have no discontinuity: compare straight against the fp64 oracle."""
+    for name in ("cross_b3", "fuse_b8", "cross_home_b3", "fuse_home_b8"):
+        case = C.CASES_BY_NAME[name]
+        o_out, _, _ = C.run_oracle(case, torch.float64)
+        c_out, _, _ = PU.run_cuda(case, "bf16")
+        for a, b in zip(c_out, o_out):
+            assert PU.nerr(a, b) <= PU.TOL["bf16"], name
+
+
+def test_gate_argmax_identical_in_fp32():
+    """north_star: gate argmax bit-identical on the fp32 path (wherever the fp64 top-2 margin exceeds 1e-5,
+    i.e. beyond what any fp32 summation order can resolve — SURVEY.md §7.2)."""
+    from oracle import mmoe_oracle as O
+    case = C.CASES_BY_NAME["head_b256"]
+    mod = PU.build_module(case)
+    (ev,) = case.inputs()
+    wg, wb = mod.gate_weights(ev.cuda())
+    sd64 = {k: v.double() for k, v in case.state_dict().items()}
+    _, _, rg, rb = O.two_task_mmoe(sd64, ev.double(), return_gates=True)
+    for w, r in ((wg, rg), (wb, rb)):
+        top = r.topk(2, -1).values
+        safe = (top[:, 0] - top[:, 1]) > 1e-5
+        assert safe.float().mean() > 0.99
+        assert (w.cpu().argmax(-1)[safe] == r.argmax(-1)[safe]).all()
+        assert float((w.cpu().double() - r).abs().max()) < 1e-6
+    # the stand-alone DenseGate module agrees with the fused kernel
+    w2 = mod.gate_good(ev.cuda().mean(1))
+    assert float((w2 - wg).abs().max()) < 1e-6
+
+
+def test_scoring_order_matches_in_fp32():
+    """AUC ordering on the fp32 path: ranks of the logits equal the oracle's except for pairs closer than fp32 noise."""
+    from oracle import mmoe_oracle as O
+    case = C.Case("head_b4096", "head", 4096, 77)
+    mod = PU.build_module(case)
+    (ev,) = case.inputs()
+    with torch.no_grad():
+        lg, lb = mod(ev.cuda())
+    sd64 = {k: v.double() for k, v in case.state_dict().items()}
+    rg, rb = O.two_task_mmoe(sd64, ev.double())
+    for a, r in ((lg, rg), (lb, rb)):
+        a = a.cpu().double()
+        assert float((a - r).abs().max()) <= 1e-4 * float(r.abs().max())
+        order_a, order_r = a.argsort(), r.argsort()
+        mism = order_a != order_r
+        if mism.any():
+            # every displaced pair must be a near-tie in the oracle
+            gaps = (r[order_r][1:] - r[order_r][:-1])
+            pos = mism.nonzero().flatten()
+            lo = (pos - 1).clamp(min=0)
+            assert float(gaps[lo.clamp(max=gaps.numel() - 1)].abs().max()) < 1e-4
+
+
+def test_unused_home_parameters_keep_grad_none():
+    for name in ("cross_home_b3", "fuse_home_b8"):
+        case = C.CASES_BY_NAME[name]
+        _, _, gp = PU.run_cuda(case, "fp32")
+        unused = set(case.shapes()) - set(case.used_param_keys())
+        assert unused
+        for k in unused:
+            assert gp[k] is None
+        for k in case.used_param_keys():
+            assert gp[k] is not None
+
+
+def test_fully_masked_row_gives_nan_like_the_reference():
+    case = C.CASES_BY_NAME["cross_b3"]
+    mod = PU.build_module(case)
+    u, um, i, im = case.inputs()
+    im = im.clone()
+    im[2] = True
+    with torch.no_grad():
+        out = mod(u.cuda(), um.cuda(), i.cuda(), im.cuda()).cpu()
+    assert torch.isfinite(out[:2]).all() and torch.isnan(out[2]).all()
+
+
+def test_no_cpu_fallback():
+    case = C.CASES_BY_NAME["head_b16"]
+    mod = PU.build_module(case, device="cuda")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mod(case.inputs()[0])          # CPU tensor -> loud failure, never a silent eager path
+
+
+def test_empty_batch():
+    case = C.CASES_BY_NAME["head_b16"]
+    mod = PU.build_module(case)
+    lg, lb = mod(torch.zeros(0, 6, 768, device="cuda"))
+    assert lg.shape == (0,) and lb.shape == (0,)
+
+
+def test_train_mode_dropout_statistics_and_determinism():
+    """Train mode: dropout masks come from a keyed counter hash; same torch seed -> same result, the keep rate is 1-p,
+    and the backward pass regenerates the same mask (gradient of a dropped unit is exactly zero)."""
+    import ctypes as Ct
+    import mmoe_multimodal_rec_b200 as pkg
+    L = pkg.lib()
+    n = 1 << 20
+    out = torch.empty(n, dtype=torch.uint8, device="cuda")
+    assert L.mmoe_dropout_mask(123, 456, 0.1, n, out.data_ptr(), torch.cuda.current_stream().cuda_stream) == 0
+    keep = out.float().mean().item()
+    assert abs(keep - 0.9) < 2e-3
+    case = C.CASES_BY_NAME["fuse_b8"]
+    mod = PU.build_module(case).train()
+    v, t = [x.cuda() for x in case.inputs()]
+    torch.manual_seed(5); a = mod(v, t)
+    torch.manual_seed(5); b = mod(v, t)
+    torch.manual_seed(6); c = mod(v, t)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    frac_zero = (a == 0).float().mean().item()          # final Dropout(0.1) of proj
+    assert 0.05 < frac_zero < 0.16
+    v.requires_grad_(True)
+    torch.manual_seed(5)
+    out2 = mod(v, t)
+    out2.sum().backward()
+    assert torch.isfinite(v.grad).all()
