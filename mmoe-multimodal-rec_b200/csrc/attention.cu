@@ -8,6 +8,8 @@
 //
 // This is the exact-arithmetic (fp32 FFMA) implementation, used for MMOE_F32 and as the
 // cross-check of the tensor-core variant.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace mmoe {
@@ -220,8 +222,14 @@ static int launch_bwd(const AttnDev& d, cudaStream_t s) {
   return 0;
 }
 
+static bool force_exact() {
+  static const bool f = getenv("MMOE_DEBUG_FORCE_SIMT") != nullptr;   // test-only cross-check switch
+  return f;
+}
+
 int attention_fwd(const AttnArgs& a, cudaStream_t s) {
   if (a.B == 0) return 0;
+  if (!force_exact() && attention_tc_supported(a)) return attention_tc(a, false, s);
   AttnDev d;
   MMOE_TRY(fill(&d, a));
   if (a.dtype == MMOE_BF16) return launch_fwd<__nv_bfloat16>(d, s);
@@ -230,6 +238,7 @@ int attention_fwd(const AttnArgs& a, cudaStream_t s) {
 }
 int attention_bwd(const AttnArgs& a, cudaStream_t s) {
   if (a.B == 0) return 0;
+  if (!force_exact() && attention_tc_supported(a)) return attention_tc(a, true, s);
   AttnDev d;
   MMOE_TRY(fill(&d, a));
   if (a.dtype == MMOE_BF16) return launch_bwd<__nv_bfloat16>(d, s);

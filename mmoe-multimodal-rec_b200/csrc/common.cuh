@@ -102,21 +102,20 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---------------------------------------------------------------- dropout keep-mask
-// A counter-based hash of the flat element index, keyed per dropout site.  Any kernel can
-// regenerate the mask in backward from (key0, key1, index); no mask tensor is ever stored.
-__host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
-  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
-  return h;
+// A counter-based hash of the flat element index, keyed per dropout site.  Any kernel can regenerate the mask in
+// backward from (key0, key1, index); no mask tensor is ever stored.  One 32-bit hash serves the element PAIR
+// (2i, 2i+1): 16 bits each, keep iff bits >= p * 2^16  (p = 0.1 -> 6553/65536 = 0.09999).
+__host__ __device__ __forceinline__ uint32_t drop_hash(uint32_t key0, uint32_t key1, uint64_t pair_idx) {
+  uint32_t x = ((uint32_t)pair_idx ^ ((uint32_t)(pair_idx >> 32) * 0x632BE5ABu) ^ key0) * 0x9E3779B1u;
+  x ^= x >> 15; x *= 0x85EBCA77u;
+  x ^= x >> 13; x = (x ^ key1) * 0xC2B2AE3Du;
+  x ^= x >> 16;
+  return x;
 }
-__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
-  // keep iff (hash >> 8) >= p * 2^24
-  return (uint32_t)(p * 16777216.0f);
-}
+__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) { return (uint32_t)(p * 65536.0f); }
 __host__ __device__ __forceinline__ bool drop_keep(uint32_t key0, uint32_t key1, uint64_t idx, uint32_t thresh) {
-  uint32_t x = (uint32_t)idx ^ ((uint32_t)(idx >> 32) * 0x632BE5ABu);
-  uint32_t h = mix32((x ^ key0) * 0x9E3779B1u);
-  h = mix32(h ^ key1);
-  return (h >> 8) >= thresh;
+  const uint32_t h = drop_hash(key0, key1, idx >> 1);
+  return ((h >> ((uint32_t)(idx & 1) * 16)) & 0xFFFFu) >= thresh;
 }
 // per-site keys derived on the host from the call seed
 inline void site_keys(uint64_t seed, uint32_t site, uint32_t* k0, uint32_t* k1) {

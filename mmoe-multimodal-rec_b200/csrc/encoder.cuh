@@ -13,13 +13,15 @@
 
 namespace mmoe {
 
+// Bump allocator over a caller-owned blob.  With a null base it only measures: the "pointers" it returns are then
+// the byte offsets themselves (used by the *_bytes size queries and the *_saved_offset layout queries).
 struct Arena {
-  char* base;
+  uintptr_t base;
   size_t off;
-  explicit Arena(void* b) : base(reinterpret_cast<char*>(b)), off(0) {}
+  explicit Arena(void* b) : base(reinterpret_cast<uintptr_t>(b)), off(0) {}
   void* take(size_t bytes) {
     off = (off + 255) & ~(size_t)255;
-    void* p = base ? base + off : nullptr;
+    void* p = reinterpret_cast<void*>(base + off);
     off += bytes;
     return p;
   }

@@ -207,11 +207,20 @@ constexpr int TBM = 128, TBN = 256, TBK = 64, TSTAGES = 4;
 constexpr int TA_BYTES = TBM * TBK * 2;   // 16 KB
 constexpr int TB_BYTES = TBN * TBK * 2;   // 32 KB
 constexpr int TSTAGE_BYTES = TA_BYTES + TB_BYTES;
-constexpr int TEPI_PITCH = 33;
-constexpr int TEPI_BYTES = 4 * 32 * TEPI_PITCH * 4;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TEPI_PITCH = 34;            // even: float2 reads stay 8-byte aligned
+constexpr int TEPI_BYTES = TC_EPI_WARPS * 32 * TEPI_PITCH * 4;
 constexpr int TC_SMEM_BYTES = 1024 /*align slack*/ + TSTAGES * TSTAGE_BYTES + TEPI_BYTES + 256 /*barriers*/;
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 128 + 32 * TC_EPI_WARPS;
 
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -318,7 +327,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -397,40 +406,123 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue warps (TMEM -> regs -> smem transpose -> global) =====================
-    const int quad = warp & 3;              // TMEM lane quadrant this warp may read
-    float* st = epi_stage + quad * 32 * TEPI_PITCH;
+    // ===================== epilogue: 8 warps (TMEM -> regs -> smem transpose -> fused epilogue -> global) ==========
+    // Warp w may read TMEM lanes 32*(w%4)..+31 (its quadrant of the 128 accumulator rows); the two warps of a quadrant
+    // split the 256 columns.  After the transpose through a private smem slab a lane owns 2 ADJACENT columns and a
+    // half-warp owns one row, so a warp instruction touches 2 rows x 32 columns: 64 B (16-bit) / 128 B (fp32) segments.
+    const int ew = warp - 4;
+    const int quad = warp & 3;
+    const int half = ew >> 2;
+    float* st = epi_stage + ew * 32 * TEPI_PITCH;
+    const int sub = lane >> 4;               // row of the pair this half-warp handles
+    const int cl = (lane & 15) * 2;          // first of the lane's two columns inside a 32-column chunk
     int as = 0; uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileInfo t = decode_tile(p, tile);
       const TcGroup& g = p.g[t.gi];
+      const EpiDev& E = g.epi;
       const int m0 = t.m_blk * TBM + quad * 32, n0 = t.n_blk * TBN;
       const bool first = (t.split == 0);
+      const int N = g.N;
+      const int rows = min(32, g.M - m0);    // may be <= 0 for a ragged last tile
+      // hoist the epilogue description into registers
+      const mmoe_epilogue& e = E.e;
+      char* const out = reinterpret_cast<char*>(e.out);
+      char* const preact = reinterpret_cast<char*>(e.preact);
+      const char* const aux = reinterpret_cast<const char*>(e.aux);
+      const float* const residual = first ? e.residual : nullptr;
+      const float* const bias = first ? e.bias : nullptr;
+      float* const colsum = e.colsum;
+      const int64_t ldo = e.ldo, ld_aux = e.ld_aux, ld_res = e.ld_res;
+      const float alpha = e.alpha, dscale = E.drop_scale;
+      const int act = e.act, bwd_mode = e.bwd_mode;
+      const bool out_f32 = e.out_dtype == MMOE_F32, accumulate = e.accumulate != 0, is_bf16 = E.op_dtype == MMOE_BF16;
+      const uint32_t thresh = (e.drop_p > 0.0f && bwd_mode != 1) ? E.thresh : 0u;
+      const uint32_t dk0 = e.drop_key0, dk1 = e.drop_key1;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const int rows = min(32, g.M - m0);   // may be <= 0 for a ragged last tile
 #pragma unroll 1
-      for (int c = 0; c < TBN / 32; ++c) {
-        const int nb = n0 + c * 32;
-        if (nb >= g.N) break;
+      for (int c = 0; c < 4; ++c) {
+        const int col0 = half * 128 + c * 32;
+        const int nb = n0 + col0;
+        if (nb >= N) break;
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * TBN + c * 32), v);
-        if (rows > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * TBN + col0), v);
+        if (rows <= 0) continue;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) st[lane * TEPI_PITCH + j] = __uint_as_float(v[j]);
-          __syncwarp();
-          const int n = nb + lane;
-          if (n < g.N) {
-            float csum = 0.0f;
-            for (int r = 0; r < rows; ++r) {
-              const float val = epi_value(g.epi, g.N, m0 + r, n, st[r * TEPI_PITCH + lane], first);
-              csum += val;
-              epi_store(g.epi, m0 + r, n, val);
+        for (int j = 0; j < 32; ++j) st[lane * TEPI_PITCH + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        const int n = nb + cl;
+        const bool n_ok = n < N;               // N is even on this path, so the pair is in or out together
+        float2 b2 = make_float2(0.f, 0.f);
+        if (bias != nullptr && n_ok) b2 = *reinterpret_cast<const float2*>(bias + n);
+        float cs0 = 0.f, cs1 = 0.f;
+#pragma unroll 1
+        for (int rp0 = 0; rp0 < 16; rp0 += 4) {
+          float2 acc[4], res[4];
+          uint32_t ax[4];
+          bool ok[4];
+          // phase 1: all loads of the 4 row pairs in flight together
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = (rp0 + u) * 2 + sub;
+            ok[u] = n_ok && r < rows;
+            acc[u] = *reinterpret_cast<const float2*>(st + r * TEPI_PITCH + cl);
+            res[u] = make_float2(0.f, 0.f);
+            ax[u] = 0u;
+            if (ok[u]) {
+              const int64_t m = m0 + r;
+              if (residual != nullptr) res[u] = *reinterpret_cast<const float2*>(residual + m * ld_res + n);
+              if (bwd_mode != 0) ax[u] = *reinterpret_cast<const uint32_t*>(aux + (m * ld_aux + n) * 2);
             }
-            if (g.epi.e.colsum != nullptr) atomicAdd(g.epi.e.colsum + n, csum);
           }
-          __syncwarp();
+          // phase 2: math + stores
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (!ok[u]) continue;
+            const int r = (rp0 + u) * 2 + sub;
+            const int64_t m = m0 + r;
+            float v0 = fmaf(alpha, acc[u].x, b2.x), v1 = fmaf(alpha, acc[u].y, b2.y);
+            if (preact != nullptr) {
+              const uint32_t pk = is_bf16 ? pack_bf16(v0, v1) : pack_f16(v0, v1);
+              *reinterpret_cast<uint32_t*>(preact + (m * ldo + n) * 2) = pk;
+            }
+            if (act == 1) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+            else if (act == 2) { v0 = gelu_f(v0); v1 = gelu_f(v1); }
+            else if (act == 3) { v0 = sigmoid_f(v0); v1 = sigmoid_f(v1); }
+            if (bwd_mode != 0) {
+              float a0, a1;
+              if (is_bf16) { a0 = __uint_as_float(ax[u] << 16); a1 = __uint_as_float(ax[u] & 0xFFFF0000u); }
+              else { const __half2 hh = *reinterpret_cast<const __half2*>(&ax[u]); a0 = __low2float(hh); a1 = __high2float(hh); }
+              if (bwd_mode == 1) { v0 = (a0 != 0.f) ? v0 * dscale : 0.f; v1 = (a1 != 0.f) ? v1 * dscale : 0.f; }
+              else if (bwd_mode == 2) { v0 *= gelu_grad_f(a0); v1 *= gelu_grad_f(a1); }
+              else { const float s0 = sigmoid_f(a0), s1 = sigmoid_f(a1); v0 *= s0 * (1.f - s0); v1 *= s1 * (1.f - s1); }
+            }
+            if (thresh != 0u) {
+              const uint32_t h = drop_hash(dk0, dk1, ((uint64_t)m * (uint64_t)N + (uint64_t)n) >> 1);
+              v0 = ((h & 0xFFFFu) >= thresh) ? v0 * dscale : 0.f;
+              v1 = ((h >> 16) >= thresh) ? v1 * dscale : 0.f;
+            }
+            v0 += res[u].x; v1 += res[u].y;
+            cs0 += v0; cs1 += v1;
+            if (out != nullptr) {
+              if (accumulate) {
+                float* o = reinterpret_cast<float*>(out) + m * ldo + n;
+                atomicAdd(o, v0); atomicAdd(o + 1, v1);
+              } else if (out_f32) {
+                *reinterpret_cast<float2*>(reinterpret_cast<float*>(out) + m * ldo + n) = make_float2(v0, v1);
+              } else {
+                *reinterpret_cast<uint32_t*>(out + (m * ldo + n) * 2) = is_bf16 ? pack_bf16(v0, v1) : pack_f16(v0, v1);
+              }
+            }
+          }
         }
+        if (colsum != nullptr) {
+          cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16);
+          cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
+          if (sub == 0 && n_ok) { atomicAdd(colsum + n, cs0); atomicAdd(colsum + n + 1, cs1); }
+        }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -616,6 +708,18 @@ static int gemm_grouped_untimed(const mmoe_gemm_problem* problems, int n_problem
   if (dtype == MMOE_F32) return launch_simt<float>(problems, n_problems, dtype, stream);
   static const bool force_simt = getenv("MMOE_DEBUG_FORCE_SIMT") != nullptr;   // test-only cross-check switch
   if (engine == 1 || force_simt) {
+    if (dtype == MMOE_BF16) return launch_simt<__nv_bfloat16>(problems, n_problems, dtype, stream);
+    return launch_simt<__half>(problems, n_problems, dtype, stream);
+  }
+  // the tensor-core epilogue moves column PAIRS: it needs even N and even leading dimensions
+  bool pair_ok = true;
+  for (int i = 0; i < n_problems; ++i) {
+    const mmoe_epilogue& e = problems[i].epi;
+    if ((problems[i].N & 1) || (e.ldo & 1) || (e.bwd_mode != 0 && (e.ld_aux & 1)) || (e.residual != nullptr && (e.ld_res & 1)) ||
+        (e.out != nullptr && (reinterpret_cast<uintptr_t>(e.out) & 7)) || (e.bias != nullptr && (reinterpret_cast<uintptr_t>(e.bias) & 7)))
+      pair_ok = false;
+  }
+  if (!pair_ok) {
     if (dtype == MMOE_BF16) return launch_simt<__nv_bfloat16>(problems, n_problems, dtype, stream);
     return launch_simt<__half>(problems, n_problems, dtype, stream);
   }

@@ -45,6 +45,9 @@ struct AttnArgs {
   float drop_p; uint32_t k0, k1;
   int dtype;
 };
+// tensor-core (mma.sync) variant for the 16-bit modes, attention_tc.cu
+bool attention_tc_supported(const AttnArgs& a);
+int attention_tc(const AttnArgs& a, bool bwd, cudaStream_t s);
 int attention_fwd(const AttnArgs& a, cudaStream_t s);
 int attention_bwd(const AttnArgs& a, cudaStream_t s);
 
