@@ -210,7 +210,7 @@ constexpr int TSTAGE_BYTES = TA_BYTES + TB_BYTES;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TEPI_PITCH = 34;            // even: float2 reads stay 8-byte aligned
 constexpr int TEPI_BYTES = TC_EPI_WARPS * 32 * TEPI_PITCH * 4;
-constexpr int TC_SMEM_BYTES = 1024 /*align slack*/ + TSTAGES * TSTAGE_BYTES + TEPI_BYTES + 256 /*barriers*/;
+constexpr int TC_SMEM_BYTES = TSTAGES * TSTAGE_BYTES + TEPI_BYTES + 128 /*barriers + TMEM slot*/;   // 231,552 B of the 232,448 B limit
 constexpr int TC_THREADS = 128 + 32 * TC_EPI_WARPS;
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -308,9 +308,12 @@ __device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int tile) {
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  // SWIZZLE_128B tiles need 1024-byte alignment; the kernel has no static shared memory, so the dynamic window starts
+  // at the (aligned) base of the CTA's shared memory.  Checked, not assumed.
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0u) __trap();
+  uint8_t* smem_gen = smem_raw;
   const uint32_t smem_a0 = smem_base;
   const uint32_t smem_b0 = smem_base + TSTAGES * TA_BYTES;
   float* epi_stage = reinterpret_cast<float*>(smem_gen + TSTAGES * TSTAGE_BYTES);
