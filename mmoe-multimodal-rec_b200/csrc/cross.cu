@@ -167,6 +167,7 @@ static CrossIdx cross_idx(int n_layer) {
 
 struct CrossSaved {
   EncSaved user[4], item[4];
+  float *U, *I;
   void *Ut, *It, *q, *kv, *ctx, *c;
   float* w_pool; float* pooled;
   float *normed_f, *st; void *normed_t, *z, *h;
@@ -176,6 +177,7 @@ static CrossSaved cross_layout(Arena& A, const mmoe_cross_cfg& cfg, int B, int d
   const int64_t M = (int64_t)B * cfg.S; const int d = cfg.d, ff = 4 * cfg.d; const size_t es = dtype_size(dtype);
   for (int l = 0; l < cfg.n_layer; ++l) s.user[l] = enc_layout(A, M, d, ff, es);
   for (int l = 0; l < cfg.n_layer; ++l) s.item[l] = enc_layout(A, M, d, ff, es);
+  s.U = (float*)A.take(M * d * 4); s.I = nullptr;   // only the 16-bit copy of the item stream is needed downstream
   s.Ut = A.take(M * d * es); s.It = A.take(M * d * es);
   s.q = A.take(M * d * es); s.kv = A.take(M * 2 * d * es);
   s.ctx = A.take(M * d * es); s.c = A.take(M * d * es);
@@ -221,7 +223,7 @@ extern "C" size_t mmoe_cross_saved_bytes(const mmoe_cross_cfg* cfg, int32_t B, i
 }
 // layout query (tests / debugging): byte range of a saved activation inside the blob.
 // stream_id 0 = user stack, 1 = item stack; which: 0 = h (post ReLU/dropout FFN activation [B*S, 4d] T),
-// 1 = x2 (layer output, fp32 [B*S, d]).
+// 1 = x1 (stream after the attention block, fp32 [B*S, d]).
 extern "C" int mmoe_cross_saved_offset(const mmoe_cross_cfg* cfg, int32_t B, int dtype, int home, int stream_id, int layer, int which,
                                        size_t* offset, size_t* bytes) {
   MMOE_TRY(check_cfg(cfg, B));
@@ -231,7 +233,7 @@ extern "C" int mmoe_cross_saved_offset(const mmoe_cross_cfg* cfg, int32_t B, int
   const EncSaved& e = stream_id == 0 ? s.user[layer] : s.item[layer];
   const size_t M = (size_t)B * cfg->S;
   if (which == 0) { *offset = (size_t)(char*)e.h; *bytes = M * 4 * cfg->d * dtype_size(dtype); }
-  else if (which == 1) { *offset = (size_t)(char*)e.x2; *bytes = M * cfg->d * 4; }
+  else if (which == 1) { *offset = (size_t)(char*)e.x1; *bytes = M * cfg->d * 4; }
   else { set_error("saved_offset: unknown buffer %d", which); return -1; }
   return 0;
 }
@@ -262,22 +264,23 @@ extern "C" int mmoe_cross_fwd(const mmoe_call* c, const mmoe_cross_cfg* cfg, con
   ec.dtype = dtype; ec.M = M; ec.Bseq = B; ec.S = S; ec.d = d; ec.ff = ff; ec.H = cfg->n_head;
   ec.drop_p = drop_p; ec.seed = c->seed; ec.stream = st;
   const float* x = user;
+  const void* delta = nullptr;
   for (int l = 0; l < cfg->n_layer; ++l) {
     ec.mask = user_mask; ec.site0 = 16 * l;
-    MMOE_TRY(enc_fwd(ec, enc_w(P + ix.user0 + 12 * l), x, s.user[l]));
-    x = s.user[l].x2;
+    MMOE_TRY(enc_fwd(ec, enc_w(P + ix.user0 + 12 * l), x, delta, s.user[l]));
+    x = s.user[l].x1; delta = s.user[l].y2;
   }
-  const float* U = x;
-  x = item;
+  // stream outputs: U = x1 + y2 (fp32 for the gate mix / pooling) and its 16-bit copy (Q-projection operand)
+  MMOE_TRY(add_cast(x, delta, s.U, s.Ut, (int64_t)M * d, dtype, st));
+  const float* U = s.U;
+  x = item; delta = nullptr;
   for (int l = 0; l < cfg->n_layer; ++l) {
     ec.mask = item_mask; ec.site0 = 16 * l + 8;
-    MMOE_TRY(enc_fwd(ec, enc_w(P + ix.item0 + 12 * l), x, s.item[l]));
-    x = s.item[l].x2;
+    MMOE_TRY(enc_fwd(ec, enc_w(P + ix.item0 + 12 * l), x, delta, s.item[l]));
+    x = s.item[l].x1; delta = s.item[l].y2;
   }
-  const float* I = x;
-  // cross attention: q from the user stream, k/v from the item stream (model.py:435-440)
-  MMOE_TRY(cast_f32(U, s.Ut, (int64_t)M * d, dtype, st));
-  MMOE_TRY(cast_f32(I, s.It, (int64_t)M * d, dtype, st));
+  // cross attention: q from the user stream, k/v from the item stream (model.py:435-440); only the 16-bit copy of I is needed
+  MMOE_TRY(add_cast(x, delta, nullptr, s.It, (int64_t)M * d, dtype, st));
   const char* w_in = (const char*)P[ix.ca_w];
   const float* b_in = (const float*)P[ix.ca_b];
   {
@@ -356,7 +359,7 @@ extern "C" int mmoe_cross_bwd(const mmoe_call* c, const mmoe_cross_cfg* cfg, con
   void* const* G = c->grads;
   const float drop_p = c->training ? c->drop_p : 0.f;
   uint32_t k0, k1;
-  const float* U = s.user[cfg->n_layer - 1].x2;
+  const float* U = s.U;
 
   const float* dpooled = dout;
   if (!c->home) {
@@ -437,13 +440,13 @@ extern "C" int mmoe_cross_bwd(const mmoe_call* c, const mmoe_cross_cfg* cfg, con
   ec.drop_p = drop_p; ec.seed = c->seed; ec.stream = st;
   for (int l = cfg->n_layer - 1; l >= 0; --l) {
     ec.mask = user_mask; ec.site0 = 16 * l;
-    const float* x_in = l == 0 ? user : s.user[l - 1].x2;
+    const float* x_in = l == 0 ? user : s.user[l].x_sum;
     MMOE_TRY(enc_bwd(ec, enc_w(P + ix.user0 + 12 * l), enc_g(G + ix.user0 + 12 * l), x_in, s.user[l], t.enc, t.dU,
                      l == 0 ? d_user : t.dU));
   }
   for (int l = cfg->n_layer - 1; l >= 0; --l) {
     ec.mask = item_mask; ec.site0 = 16 * l + 8;
-    const float* x_in = l == 0 ? item : s.item[l - 1].x2;
+    const float* x_in = l == 0 ? item : s.item[l].x_sum;
     MMOE_TRY(enc_bwd(ec, enc_w(P + ix.item0 + 12 * l), enc_g(G + ix.item0 + 12 * l), x_in, s.item[l], t.enc, t.dI,
                      l == 0 ? d_item : t.dI));
   }

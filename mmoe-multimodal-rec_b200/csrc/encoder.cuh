@@ -2,9 +2,12 @@
 // nn.TransformerEncoderLayer(norm_first=True) of EnhancedCrossFuse, model.py:460-465),
 // forward and backward, as a sequence of fused launches:
 //
-//   forward  : LN1 -> [QKV GEMM +bias] -> attention -> [out-proj GEMM +bias +dropout +residual]
-//              -> LN2 -> [FFN1 GEMM +bias +ReLU +dropout] -> [FFN2 GEMM +bias +dropout +residual]
-//   backward : cast/drop(+db2) -> {dgrad FFN2 (+ReLU/drop mask, +db1) | wgrad W2} -> {dgrad FFN1 | wgrad W1}
+//   forward  : [residual add +] LN1 -> [QKV GEMM +bias] -> attention -> [out-proj GEMM +bias +dropout]
+//              -> [residual add + LN2] -> [FFN1 GEMM +bias +ReLU +dropout] -> [FFN2 GEMM +bias +dropout]
+//              Every large GEMM writes a 16-bit tile through the TMA-store epilogue; the residual adds ride on the
+//              LayerNorm kernels (x = x + delta is exactly what autocast computes: a 16-bit linear output added to the
+//              fp32 stream).  The layer's output x1 + y2 is materialised by its consumer (next LN1 / add_cast).
+//   backward : cast/drop(+db2) -> {dgrad FFN2 | wgrad W2} -> [ReLU/drop mask + db1] -> {dgrad FFN1 | wgrad W1}
 //              -> LN2' (+residual, +dropout1 mask, +d b_out) -> {dgrad out-proj | wgrad Wo}
 //              -> attention' (+d b_in) -> {dgrad QKV | wgrad W_in} -> LN1' (+residual)
 //   "{a | b}" = one grouped GEMM launch.
@@ -53,19 +56,22 @@ inline EncG enc_g(void* const* p) {
 
 // activations kept for backward
 struct EncSaved {
-  void* xn1; float* st1; void* qkv; void* ctx; float* x1; void* xn2; float* st2; void* h; float* x2;
+  float* x_sum;   // layer input when it arrived as (x_prev + delta_prev); unused for a layer fed directly
+  void* xn1; float* st1; void* qkv; void* ctx; void* y1; float* x1; void* xn2; float* st2; void* h; void* y2;
 };
 inline EncSaved enc_layout(Arena& A, int64_t M, int d, int ff, size_t es) {
   EncSaved s;
+  s.x_sum = (float*)A.take(M * d * sizeof(float));
   s.xn1 = A.take(M * d * es);
   s.st1 = (float*)A.take(M * 2 * sizeof(float));
   s.qkv = A.take(M * 3 * d * es);
   s.ctx = A.take(M * d * es);
+  s.y1 = A.take(M * d * es);
   s.x1 = (float*)A.take(M * d * sizeof(float));
   s.xn2 = A.take(M * d * es);
   s.st2 = (float*)A.take(M * 2 * sizeof(float));
   s.h = A.take(M * ff * es);
-  s.x2 = (float*)A.take(M * d * sizeof(float));
+  s.y2 = A.take(M * d * es);
   return s;
 }
 // scratch of the backward pass
@@ -115,11 +121,18 @@ inline mmoe_gemm_problem linear_wgrad(const void* dy, int64_t lddy, const void* 
   return gemm_problem(dy, lddy, 1, x, ldx, 1, N, K, M, e, wgrad_splits(N, K, M));
 }
 
-inline int enc_fwd(const EncCtx& c, const EncW& w, const float* x_in, const EncSaved& s) {
+// x_prev (+ delta_prev, 16-bit, may be null) is the layer input.  On return the layer output is s.x1 + s.y2 (pending).
+inline int enc_fwd(const EncCtx& c, const EncW& w, const float* x_prev, const void* delta_prev, const EncSaved& s) {
   const int d = c.d, ff = c.ff; const int M = (int)c.M;
   const size_t es = dtype_size(c.dtype);
   uint32_t k0, k1;
-  MMOE_TRY(layernorm_fwd(x_in, MMOE_F32, w.ln1_w, w.ln1_b, s.xn1, nullptr, s.st1, M, d, c.dtype, c.stream));
+  const float* x_in = x_prev;
+  if (delta_prev != nullptr) {
+    MMOE_TRY(layernorm_fwd_add(x_prev, delta_prev, s.x_sum, w.ln1_w, w.ln1_b, s.xn1, s.st1, M, d, c.dtype, c.stream));
+    x_in = s.x_sum;
+  } else {
+    MMOE_TRY(layernorm_fwd(x_prev, MMOE_F32, w.ln1_w, w.ln1_b, s.xn1, nullptr, s.st1, M, d, c.dtype, c.stream));
+  }
   {
     mmoe_epilogue e = epi_none();
     e.out = s.qkv; e.out_dtype = c.dtype; e.ldo = 3 * d; e.bias = w.b_in;
@@ -136,14 +149,15 @@ inline int enc_fwd(const EncCtx& c, const EncW& w, const float* x_in, const EncS
     MMOE_TRY(attention_fwd(a, c.stream));
   }
   {
-    mmoe_epilogue e = epi_none();
-    e.out = s.x1; e.out_dtype = MMOE_F32; e.ldo = d; e.bias = w.b_out; e.residual = x_in; e.ld_res = d;
+    mmoe_epilogue e = epi_none();       // y1 = drop1(ctx Wo^T + bo)
+    e.out = s.y1; e.out_dtype = c.dtype; e.ldo = d; e.bias = w.b_out;
     site_keys(c.seed, c.site0 + 1, &k0, &k1);
     e.drop_p = c.drop_p; e.drop_key0 = k0; e.drop_key1 = k1;
     mmoe_gemm_problem p = linear_fwd(s.ctx, d, w.w_out, M, d, d, e);
     MMOE_TRY(gemm_grouped(&p, 1, c.dtype, 0, c.stream));
   }
-  MMOE_TRY(layernorm_fwd(s.x1, MMOE_F32, w.ln2_w, w.ln2_b, s.xn2, nullptr, s.st2, M, d, c.dtype, c.stream));
+  // x1 = x_in + y1 ; xn2 = LN2(x1)
+  MMOE_TRY(layernorm_fwd_add(x_in, s.y1, s.x1, w.ln2_w, w.ln2_b, s.xn2, s.st2, M, d, c.dtype, c.stream));
   {
     mmoe_epilogue e = epi_none();
     e.out = s.h; e.out_dtype = c.dtype; e.ldo = ff; e.bias = w.b1; e.act = 1;
@@ -153,8 +167,8 @@ inline int enc_fwd(const EncCtx& c, const EncW& w, const float* x_in, const EncS
     MMOE_TRY(gemm_grouped(&p, 1, c.dtype, 0, c.stream));
   }
   {
-    mmoe_epilogue e = epi_none();
-    e.out = s.x2; e.out_dtype = MMOE_F32; e.ldo = d; e.bias = w.b2; e.residual = s.x1; e.ld_res = d;
+    mmoe_epilogue e = epi_none();       // y2 = drop2(h W2^T + b2)
+    e.out = s.y2; e.out_dtype = c.dtype; e.ldo = d; e.bias = w.b2;
     site_keys(c.seed, c.site0 + 3, &k0, &k1);
     e.drop_p = c.drop_p; e.drop_key0 = k0; e.drop_key1 = k1;
     mmoe_gemm_problem p = linear_fwd(s.h, ff, w.w2, M, d, ff, e);
@@ -174,11 +188,12 @@ inline int enc_bwd(const EncCtx& c, const EncW& w, const EncG& g, const float* x
   MMOE_TRY(cast_drop_colsum(dy, t.g, g.b2, M, d, c.drop_p, k0, k1, c.dtype, c.stream));
   {
     mmoe_epilogue e = epi_none();
-    e.out = t.dh; e.out_dtype = c.dtype; e.ldo = ff; e.bwd_mode = 1; e.aux = s.h; e.ld_aux = ff; e.colsum = g.b1;
-    e.drop_p = c.drop_p;   // only the 1/(1-p) scale is used in bwd_mode 1 (the mask is h != 0)
+    e.out = t.dh; e.out_dtype = c.dtype; e.ldo = ff;
     mmoe_gemm_problem p[2] = {linear_dgrad(t.g, d, w.w2, M, d, ff, e), linear_wgrad(t.g, d, s.h, ff, g.w2, M, d, ff)};
     MMOE_TRY(gemm_grouped(p, 2, c.dtype, 0, c.stream));
   }
+  // ReLU (+dropout) backward: the kept/active pattern is h != 0; also yields d b1
+  MMOE_TRY(relu_mask_colsum(t.dh, s.h, g.b1, M, ff, c.drop_p > 0.f ? 1.f / (1.f - c.drop_p) : 1.f, c.dtype, c.stream));
   // FFN1: h = drop(relu(xn2 W1^T + b1))
   {
     mmoe_epilogue e = epi_none();

@@ -113,7 +113,7 @@ static FuseIdx fuse_idx(int depth) {
 
 struct FuseSaved {
   float* x0; void* xt0; float* r; float* st_r; float* identity; EncSaved layer[4];
-  void* xt; void* zg; void* ga; float* g; float* y; float* st_y; void* yn; void* zp;
+  float* xl; void* xt; void* zg; void* ga; float* g; float* y; float* st_y; void* yn; void* zp;
 };
 static FuseSaved fuse_layout(Arena& A, const mmoe_fuse_cfg& cfg, int B, int dtype, int home) {
   FuseSaved s{};
@@ -121,7 +121,7 @@ static FuseSaved fuse_layout(Arena& A, const mmoe_fuse_cfg& cfg, int B, int dtyp
   s.x0 = (float*)A.take(Bz * 2 * d * 4); s.xt0 = A.take(Bz * 2 * d * es);
   s.r = (float*)A.take(Bz * d * 4); s.st_r = (float*)A.take(Bz * 2 * 4); s.identity = (float*)A.take(Bz * d * 4);
   for (int l = 0; l < cfg.depth; ++l) s.layer[l] = enc_layout(A, (int64_t)2 * B, d, 4 * d, es);
-  s.xt = A.take(Bz * 2 * d * es); s.zg = A.take(Bz * (d / 2) * es); s.ga = A.take(Bz * (d / 2) * es);
+  s.xl = (float*)A.take(Bz * 2 * d * 4); s.xt = A.take(Bz * 2 * d * es); s.zg = A.take(Bz * (d / 2) * es); s.ga = A.take(Bz * (d / 2) * es);
   s.g = (float*)A.take(Bz * 4); s.y = (float*)A.take(Bz * d * 4);
   if (!home) { s.st_y = (float*)A.take(Bz * 2 * 4); s.yn = A.take(Bz * d * es); s.zp = A.take(Bz * d * es); }
   return s;
@@ -169,12 +169,14 @@ static int fuse_fwd_t(const mmoe_call* c, const mmoe_fuse_cfg* cfg, const float*
   ec.dtype = dtype; ec.M = 2 * (int64_t)B; ec.Bseq = B; ec.S = 2; ec.d = d; ec.ff = 4 * d; ec.H = cfg->n_head;
   ec.mask = nullptr; ec.drop_p = drop_p; ec.seed = c->seed; ec.stream = st;
   const float* x = s.x0;
+  const void* delta = nullptr;
   for (int l = 0; l < cfg->depth; ++l) {
     ec.site0 = 16 * l;
-    MMOE_TRY(enc_fwd(ec, enc_w(P + ix.layer0 + 12 * l), x, s.layer[l]));
-    x = s.layer[l].x2;
+    MMOE_TRY(enc_fwd(ec, enc_w(P + ix.layer0 + 12 * l), x, delta, s.layer[l]));
+    x = s.layer[l].x1; delta = s.layer[l].y2;
   }
-  MMOE_TRY(cast_f32(x, s.xt, (int64_t)B * 2 * d, dtype, st));
+  MMOE_TRY(add_cast(x, delta, s.xl, s.xt, (int64_t)B * 2 * d, dtype, st));
+  x = s.xl;
   {
     mmoe_epilogue e = epi_none();
     e.out = s.ga; e.out_dtype = dtype; e.ldo = dh; e.bias = (const float*)P[ix.g0_b]; e.act = 2; e.preact = s.zg;
@@ -213,7 +215,7 @@ static int fuse_bwd_t(const mmoe_call* c, const mmoe_fuse_cfg* cfg, const float*
   void* const* G = c->grads;
   const float drop_p = c->training ? c->drop_p : 0.f;
   uint32_t k0, k1;
-  const float* x_last = s.layer[cfg->depth - 1].x2;
+  const float* x_last = s.xl;
   const float* dy = dout;
   if (!c->home) {
     site_keys(c->seed, 100, &k0, &k1);
@@ -252,7 +254,7 @@ static int fuse_bwd_t(const mmoe_call* c, const mmoe_fuse_cfg* cfg, const float*
   ec.mask = nullptr; ec.drop_p = drop_p; ec.seed = c->seed; ec.stream = st;
   for (int l = cfg->depth - 1; l >= 0; --l) {
     ec.site0 = 16 * l;
-    const float* x_in = l == 0 ? s.x0 : s.layer[l - 1].x2;
+    const float* x_in = l == 0 ? s.x0 : s.layer[l].x_sum;
     MMOE_TRY(enc_bwd(ec, enc_w(P + ix.layer0 + 12 * l), enc_g(G + ix.layer0 + 12 * l), x_in, s.layer[l], t.enc, t.dX, t.dX));
   }
   // identity = LN(res_proj(cat)); its gradient is dy

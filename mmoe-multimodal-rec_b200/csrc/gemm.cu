@@ -77,7 +77,9 @@ __device__ __forceinline__ void epi_store(const EpiDev& d, int m, int n, float v
 struct alignas(64) TcGroup {
   CUtensorMap tma_a;
   CUtensorMap tma_b;
+  CUtensorMap tma_out;   // kind 1 only: 16-bit output, box {64 cols, 32 rows}, 128B swizzle
   EpiDev epi;
+  int kind;              // 0 = general epilogue, 1 = fast 16-bit epilogue (bias, ReLU, dropout) through TMA store
   int M, N, K;
   int tiles_m, tiles_n, k_splits, kb_total, kb_per_split;
   int tile_begin;
@@ -208,9 +210,9 @@ constexpr int TA_BYTES = TBM * TBK * 2;   // 16 KB
 constexpr int TB_BYTES = TBN * TBK * 2;   // 32 KB
 constexpr int TSTAGE_BYTES = TA_BYTES + TB_BYTES;
 constexpr int TC_EPI_WARPS = 8;
-constexpr int TEPI_PITCH = 34;            // even: float2 reads stay 8-byte aligned
-constexpr int TEPI_BYTES = TC_EPI_WARPS * 32 * TEPI_PITCH * 4;
-constexpr int TC_SMEM_BYTES = TSTAGES * TSTAGE_BYTES + TEPI_BYTES + 128 /*barriers + TMEM slot*/;   // 231,552 B of the 232,448 B limit
+constexpr int TEPI_WARP_BYTES = 4096;     // per-warp staging slab: 32 rows x 128 B
+constexpr int TEPI_BYTES = TC_EPI_WARPS * TEPI_WARP_BYTES;
+constexpr int TC_SMEM_BYTES = TSTAGES * TSTAGE_BYTES + TEPI_BYTES + 128 /*barriers + TMEM slot*/;   // 229,504 B of the 232,448 B limit
 constexpr int TC_THREADS = 128 + 32 * TC_EPI_WARPS;
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -253,6 +255,27 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -416,7 +439,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     const int ew = warp - 4;
     const int quad = warp & 3;
     const int half = ew >> 2;
-    float* st = epi_stage + ew * 32 * TEPI_PITCH;
+    float* st = epi_stage + ew * (TEPI_WARP_BYTES / 4);      // 32 x 32 fp32 slab (general path) / 32 x 128 B rows (fast path)
+    const uint32_t st_addr = smem_u32(st);
+    bool store_pending = false;
     const int sub = lane >> 4;               // row of the pair this half-warp handles
     const int cl = (lane & 15) * 2;          // first of the lane's two columns inside a 32-column chunk
     int as = 0; uint32_t aphase = 0;
@@ -444,6 +469,69 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const uint32_t dk0 = e.drop_key0, dk1 = e.drop_key1;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
+      if (g.kind == 1) {
+        // ---------- fast 16-bit epilogue: the thread keeps its accumulator row, applies bias / ReLU / dropout in
+        // registers, writes the 16-bit row into the 128B-swizzled slab and one lane issues a TMA store of the
+        // 32 x 64 block (rows >= M and columns >= N are clipped by the tensor map: no predicates anywhere).
+        const int64_t m = m0 + lane;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          const int col0 = half * 128 + c * 64;
+          const int nb = n0 + col0;
+          if (nb >= N) break;
+          uint32_t v[64];
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * TBN + col0);
+          tmem_ld32_nowait(taddr, v);
+          tmem_ld32_nowait(taddr + 32, v + 32);
+          float bl = 0.f, bh = 0.f;              // lane j holds bias[nb + j] and bias[nb + 32 + j]
+          if (bias != nullptr) {
+            if (nb + lane < N) bl = __ldg(bias + nb + lane);
+            if (nb + 32 + lane < N) bh = __ldg(bias + nb + 32 + lane);
+          }
+          tmem_ld_wait();
+          uint32_t pk[32];
+          const uint64_t idx0 = (uint64_t)m * (uint64_t)N + (uint64_t)nb;     // even (N and nb are even)
+#pragma unroll
+          for (int j = 0; j < 64; j += 2) {
+            float v0 = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, j < 32 ? bl : bh, j & 31);
+            float v1 = __uint_as_float(v[j + 1]) + __shfl_sync(0xffffffffu, j < 32 ? bl : bh, (j + 1) & 31);
+            if (act == 1) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+            if (thresh != 0u) {
+              const uint32_t h = drop_hash(dk0, dk1, (idx0 + j) >> 1);
+              v0 = ((h & 0xFFFFu) >= thresh) ? v0 * dscale : 0.f;
+              v1 = ((h >> 16) >= thresh) ? v1 * dscale : 0.f;
+            }
+            pk[j >> 1] = is_bf16 ? pack_bf16(v0, v1) : pack_f16(v0, v1);
+          }
+          if (store_pending) {                   // the previous TMA store must have finished reading the slab
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t dst = st_addr + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                         "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&g.tma_out, st_addr, nb, m0);
+            tma_store_commit();
+          }
+          store_pending = true;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+        continue;
+      }
+      if (store_pending) {                       // general path reuses the slab
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+        store_pending = false;
+      }
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         const int col0 = half * 128 + c * 32;
@@ -453,7 +541,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * TBN + col0), v);
         if (rows <= 0) continue;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) st[lane * TEPI_PITCH + j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; ++j) st[lane * 32 + ((((j >> 1) ^ (lane & 15)) << 1) | (j & 1))] = __uint_as_float(v[j]);
         __syncwarp();
         const int n = nb + cl;
         const bool n_ok = n < N;               // N is even on this path, so the pair is in or out together
@@ -470,7 +558,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           for (int u = 0; u < 4; ++u) {
             const int r = (rp0 + u) * 2 + sub;
             ok[u] = n_ok && r < rows;
-            acc[u] = *reinterpret_cast<const float2*>(st + r * TEPI_PITCH + cl);
+            acc[u] = *reinterpret_cast<const float2*>(st + r * 32 + ((((cl >> 1) ^ (r & 15))) << 1));
             res[u] = make_float2(0.f, 0.f);
             ax[u] = 0u;
             if (ok[u]) {
@@ -532,6 +620,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       if (lane == 0) mbar_arrive(tempty_bar(as));
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
+    if (store_pending && lane == 0) tma_store_wait_all();     // bulk stores must complete before the CTA's smem goes away
   }
   tc_fence_before();
   __syncthreads();
@@ -564,6 +653,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // 2-D bf16/f16 tensor [rows][cols] (cols contiguous, row stride ld elements); box {64 cols, box_rows}, 128B swizzle
 static int make_tmap(CUtensorMap* map, const void* ptr, int dtype, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  if (rows < 1) rows = 1;
   EncodeTiledFn fn = get_encode_fn();
   MMOE_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   MMOE_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "GEMM operand pointer must be 16-byte aligned");
@@ -610,6 +700,15 @@ static int launch_tc(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream_t
     if (q.b_major == 0) MMOE_TRY(make_tmap(&g.tma_b, q.b, dtype, q.N, q.K, q.ldb, TBN));
     else                MMOE_TRY(make_tmap(&g.tma_b, q.b, dtype, q.K, q.N, q.ldb, TBK));
     MMOE_TRY(fill_epi(&g.epi, q, dtype));
+    {
+      const mmoe_epilogue& e = q.epi;
+      const bool fast = e.out != nullptr && e.out_dtype != MMOE_F32 && !e.accumulate && e.preact == nullptr && e.bwd_mode == 0 &&
+                        e.residual == nullptr && e.colsum == nullptr && (e.act == 0 || e.act == 1) && e.alpha == 1.0f &&
+                        (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 && (e.ldo % 8) == 0 && q.k_splits <= 1 &&
+                        getenv("MMOE_DEBUG_GENERAL_EPILOGUE") == nullptr;
+      g.kind = fast ? 1 : 0;
+      if (fast) MMOE_TRY(make_tmap(&g.tma_out, e.out, dtype, q.M, q.N, e.ldo, 32));
+    }
     g.tiles_m = (q.M + TBM - 1) / TBM;
     g.tiles_n = (q.N + TBN - 1) / TBN;
     g.kb_total = (q.K + TBK - 1) / TBK;

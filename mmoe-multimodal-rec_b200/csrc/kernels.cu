@@ -147,7 +147,8 @@ constexpr int LN_NV = 8;   // float4 per lane -> d <= 1024
 template <typename XT, typename T>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const XT* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, T* __restrict__ y_t,
-                                                     float* __restrict__ y_f, float* __restrict__ stats, int64_t rows, int d) {
+                                                     float* __restrict__ y_f, float* __restrict__ stats, int64_t rows, int d,
+                                                     const T* __restrict__ delta = nullptr, float* __restrict__ x_sum = nullptr) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -159,8 +160,15 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const XT* __restrict__ x, c
 #pragma unroll
     for (int i = 0; i < LN_NV; ++i) {
       const int c = (i * 32 + lane) * 4;
-      if (c < d) { v[i] = load4<XT>(xr + c); sum += v[i].x + v[i].y + v[i].z + v[i].w; }
-      else v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < d) {
+        v[i] = load4<XT>(xr + c);
+        if (delta != nullptr) {
+          const float4 dl = load4<T>(delta + row * d + c);
+          v[i].x += dl.x; v[i].y += dl.y; v[i].z += dl.z; v[i].w += dl.w;
+          store4<float>(x_sum + row * d + c, v[i]);
+        }
+        sum += v[i].x + v[i].y + v[i].z + v[i].w;
+      } else v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const float mean = warp_sum(sum) * inv_d;
     float sq = 0.f;
@@ -212,6 +220,87 @@ int layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* b
   if (dtype == MMOE_BF16) return ln_fwd_dispatch<__nv_bfloat16>(x, xf, gamma, beta, y_t, y_f32, stats, rows, d, s);
   if (dtype == MMOE_F16) return ln_fwd_dispatch<__half>(x, xf, gamma, beta, y_t, y_f32, stats, rows, d, s);
   return ln_fwd_dispatch<float>(x, true, gamma, beta, y_t, y_f32, stats, rows, d, s);
+}
+
+template <typename T>
+static int ln_fwd_add_dispatch(const float* x, const void* delta, float* x_sum, const float* gamma, const float* beta, void* y_t,
+                               float* stats, int64_t rows, int d, cudaStream_t s) {
+  int64_t blocks = (rows + 7) / 8;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  ln_fwd_kernel<float, T><<<(int)blocks, 256, 0, s>>>(x, gamma, beta, (T*)y_t, nullptr, stats, rows, d, (const T*)delta, x_sum);
+  MMOE_LAUNCH_OK("ln_fwd_kernel(add)");
+  return 0;
+}
+int layernorm_fwd_add(const float* x, const void* delta, float* x_sum, const float* gamma, const float* beta, void* y_t,
+                      float* stats, int64_t rows, int d, int dtype, cudaStream_t s) {
+  if (rows == 0) return 0;
+  MMOE_CHECK(d % 4 == 0 && d <= LN_NV * 128, "layernorm: d must be a multiple of 4 and <= %d (got %d)", LN_NV * 128, d);
+  MMOE_CHECK(delta != nullptr && x_sum != nullptr, "layernorm_fwd_add: delta and x_sum are required");
+  if (dtype == MMOE_BF16) return ln_fwd_add_dispatch<__nv_bfloat16>(x, delta, x_sum, gamma, beta, y_t, stats, rows, d, s);
+  if (dtype == MMOE_F16) return ln_fwd_add_dispatch<__half>(x, delta, x_sum, gamma, beta, y_t, stats, rows, d, s);
+  return ln_fwd_add_dispatch<float>(x, delta, x_sum, gamma, beta, y_t, stats, rows, d, s);
+}
+
+// ---------------------------------------------------------------- out_f = a + b ; out_t = T(out_f)
+template <typename T>
+__global__ void add_cast_kernel(const float* __restrict__ a, const T* __restrict__ b, float* __restrict__ out_f, T* __restrict__ out_t, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    float4 v = load4<float>(a + i);
+    if (b != nullptr) { const float4 w = load4<T>(b + i); v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+    if (out_f != nullptr) store4<float>(out_f + i, v);
+    if (out_t != nullptr) store4<T>(out_t + i, v);
+  }
+}
+int add_cast(const float* a, const void* b, float* out_f, void* out_t, int64_t n, int dtype, cudaStream_t s) {
+  if (n == 0) return 0;
+  MMOE_CHECK(n % 4 == 0, "add_cast: n must be a multiple of 4");
+  int64_t blocks = (n / 4 + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (dtype == MMOE_BF16) add_cast_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, s>>>(a, (const __nv_bfloat16*)b, out_f, (__nv_bfloat16*)out_t, n);
+  else if (dtype == MMOE_F16) add_cast_kernel<__half><<<(int)blocks, 256, 0, s>>>(a, (const __half*)b, out_f, (__half*)out_t, n);
+  else add_cast_kernel<float><<<(int)blocks, 256, 0, s>>>(a, (const float*)b, out_f, (float*)out_t, n);
+  MMOE_LAUNCH_OK("add_cast_kernel");
+  return 0;
+}
+
+// ---------------------------------------------------------------- ReLU(+dropout) backward mask + bias-gradient column sums
+// block = 256 threads, panel of 64 rows; a thread owns 4 adjacent columns
+template <typename T>
+__global__ void __launch_bounds__(256) relu_mask_colsum_kernel(T* __restrict__ g, const T* __restrict__ h, float* __restrict__ colsum,
+                                                               int64_t rows, int cols, float scale) {
+  const int64_t r0 = (int64_t)blockIdx.x * 64, r1 = min(rows, r0 + 64);
+  for (int c = threadIdx.x * 4; c < cols; c += 256 * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int64_t r = r0; r < r1; ++r) {
+      const float4 hv = load4<T>(h + r * cols + c);
+      float4 gv = load4<T>(g + r * cols + c);
+      gv.x = hv.x != 0.f ? gv.x * scale : 0.f;
+      gv.y = hv.y != 0.f ? gv.y * scale : 0.f;
+      gv.z = hv.z != 0.f ? gv.z * scale : 0.f;
+      gv.w = hv.w != 0.f ? gv.w * scale : 0.f;
+      store4<T>(g + r * cols + c, gv);
+      const float4 w = load4<T>(g + r * cols + c);   // as stored (rounded)
+      acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+    }
+    if (colsum != nullptr) {
+      atomicAdd(colsum + c + 0, acc.x); atomicAdd(colsum + c + 1, acc.y);
+      atomicAdd(colsum + c + 2, acc.z); atomicAdd(colsum + c + 3, acc.w);
+    }
+  }
+}
+int relu_mask_colsum(void* g, const void* h, float* colsum, int64_t rows, int cols, float scale, int dtype, cudaStream_t s) {
+  if (rows == 0) return 0;
+  MMOE_CHECK(cols % 4 == 0, "relu_mask_colsum: cols must be a multiple of 4");
+  const int blocks = (int)((rows + 63) / 64);
+  if (dtype == MMOE_BF16) relu_mask_colsum_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((__nv_bfloat16*)g, (const __nv_bfloat16*)h, colsum, rows, cols, scale);
+  else if (dtype == MMOE_F16) relu_mask_colsum_kernel<__half><<<blocks, 256, 0, s>>>((__half*)g, (const __half*)h, colsum, rows, cols, scale);
+  else relu_mask_colsum_kernel<float><<<blocks, 256, 0, s>>>((float*)g, (const float*)h, colsum, rows, cols, scale);
+  MMOE_LAUNCH_OK("relu_mask_colsum_kernel");
+  return 0;
 }
 
 // ---------------------------------------------------------------- LayerNorm backward

@@ -16,6 +16,13 @@ int dropout_mask(uint32_t k0, uint32_t k1, float p, int64_t n, uint8_t* out, cud
 // LayerNorm forward: x fp32 or T; outputs T and/or fp32; stats [rows,2]
 int layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, void* y_t, float* y_f32, float* stats,
                   int64_t rows, int d, int dtype, cudaStream_t s);
+// Residual add fused into LayerNorm:  x_sum = x (fp32) + delta (T);  x_sum is written (fp32) and normalised into y_t.
+int layernorm_fwd_add(const float* x, const void* delta, float* x_sum, const float* gamma, const float* beta, void* y_t,
+                      float* stats, int64_t rows, int d, int dtype, cudaStream_t s);
+// out_f = a (fp32) + b (T);  out_t = T(out_f)   (either output optional)
+int add_cast(const float* a, const void* b, float* out_f, void* out_t, int64_t n, int dtype, cudaStream_t s);
+// ReLU(+dropout) backward on a stored gradient, in place:  g = (h != 0) ? g * scale : 0;  colsum += column sums of g
+int relu_mask_colsum(void* g, const void* h, float* colsum, int64_t rows, int cols, float scale, int dtype, cudaStream_t s);
 
 // LayerNorm backward fused with the residual add and the next dropout/cast:
 //   dx[r,:]  = (dres ? dres[r,:] : 0) + LN'(dy[r,:])          (fp32 out, may alias dres)

@@ -50,6 +50,16 @@ def _gemm_case(L, lib_mod, dtype_t, M, N, K, a_major, b_major, engine, variant, 
         e.out, e.out_dtype, e.ldo, e.bias, e.act = out.data_ptr(), mm, N, bias.data_ptr(), 1
         ref = torch.relu(ref + bias.double())
         keep.append(bias)
+    elif variant == "bias_drop_t":
+        bias = torch.randn(N, generator=g).to(dev)
+        out = torch.zeros(M, N, device=dev, dtype=dtype_t)
+        e.out, e.out_dtype, e.ldo, e.bias = out.data_ptr(), mm, N, bias.data_ptr()
+        e.drop_p, e.drop_key0, e.drop_key1 = 0.25, 1234567, 7654321
+        keepm = torch.empty(M * N, dtype=torch.uint8, device=dev)
+        check(L.mmoe_dropout_mask(1234567, 7654321, 0.25, M * N, keepm.data_ptr(), torch.cuda.current_stream().cuda_stream), "mask")
+        ref = (ref + bias.double()) * keepm.reshape(M, N).double() / 0.75
+        res["keep_rate"] = abs(float(keepm.float().mean()) - 0.75)
+        keep += [bias, keepm]
     elif variant == "gelu_preact_colsum":
         bias = torch.randn(N, generator=g).to(dev)
         out = torch.zeros(M, N, device=dev, dtype=dtype_t)
@@ -90,7 +100,7 @@ def gemm_checks(report, quick):
             for (am, bm) in ((0, 0), (0, 1), (1, 1), (1, 0)):
                 if (am == 1 and M % 8) or (bm == 1 and N % 8) or ((am == 0 or bm == 0) and K % 8):
                     continue
-                for variant in ("plain_f32", "bias_relu_t", "gelu_preact_colsum", "residual_f32"):
+                for variant in ("plain_f32", "bias_relu_t", "bias_drop_t", "gelu_preact_colsum", "residual_f32"):
                     if dtype_t is torch.float16 and variant != "plain_f32":
                         continue
                     for engine in ((0,) if dtype_t is torch.float32 else (0, 1)):
