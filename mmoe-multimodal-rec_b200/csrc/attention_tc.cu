@@ -71,16 +71,24 @@ __device__ __forceinline__ void frag_a_km(uint32_t (&a)[4], const T* base, int p
                : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr));
 }
 
-// global [rows][HD] (row stride ld) -> smem [64][PITCH]; rows >= valid are zero-filled.  128-bit accesses.
+// global [rows][HD] (row stride ld) -> smem [64][PITCH]; rows >= valid are zero-filled.  Asynchronous 16-byte copies
+// (cp.async, LDGSTS): every thread puts all of its chunks in flight before anyone waits, so a tile costs one memory
+// latency instead of one per chunk.
 template <typename T, int HD>
 __device__ __forceinline__ void stage_tile(T* dst, const T* src, int64_t ld, int valid, int rows_padded, int nthreads) {
   constexpr int PITCH = HD + 8, CH = HD / 8;
   for (int e = threadIdx.x; e < rows_padded * CH; e += nthreads) {
     const int r = e / CH, c = (e - r * CH) * 8;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (r < valid) v = *reinterpret_cast<const uint4*>(src + (int64_t)r * ld + c);
-    *reinterpret_cast<uint4*>(dst + r * PITCH + c) = v;
+    const bool ok = r < valid;
+    const T* g = ok ? src + (int64_t)r * ld + c : src;
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + r * PITCH + c);
+    const int bytes = ok ? 16 : 0;           // src-size 0 -> the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(g), "r"(bytes) : "memory");
   }
+}
+__device__ __forceinline__ void stage_wait() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 struct AttnTcDev {
@@ -151,6 +159,9 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcDev a) {
   stage_tile<T, HD>(Qs, (const T*)a.q + (int64_t)b * Sq * a.ldq + h * HD, a.ldq, Sq, qrows, blockDim.x);
   stage_tile<T, HD>(Ks, (const T*)a.k + (int64_t)b * Sk * a.ldk + h * HD, a.ldk, Sk, krows, blockDim.x);
   stage_tile<T, HD>(Vs, (const T*)a.v + (int64_t)b * Sk * a.ldv + h * HD, a.ldv, Sk, krows, blockDim.x);
+  __shared__ uint8_t smask[64];
+  if (a.mask != nullptr && threadIdx.x < Sk) smask[threadIdx.x] = a.mask[(int64_t)b * Sk + threadIdx.x];
+  stage_wait();
   __syncthreads();
   const int row0 = warp * 16;
   if (row0 >= Sq) return;
@@ -170,7 +181,7 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcDev a) {
       }
     }
   }
-  softmax_frag(s, NT, Sk, a.mask ? a.mask + (int64_t)b * Sk : nullptr, a.qscale, lane);
+  softmax_frag(s, NT, Sk, a.mask ? smask : nullptr, a.qscale, lane);
   if (a.thresh != 0) {
     const uint64_t base = (uint64_t)blockIdx.x * Sq * Sk;
 #pragma unroll
@@ -247,12 +258,15 @@ __global__ void __launch_bounds__(128) attn_tc_bwd_kernel(const AttnTcDev a) {
   stage_tile<T, HD>(Ks, (const T*)a.k + (int64_t)b * Sk * a.ldk + h * HD, a.ldk, Sk, krows, blockDim.x);
   stage_tile<T, HD>(Vs, (const T*)a.v + (int64_t)b * Sk * a.ldv + h * HD, a.ldv, Sk, krows, blockDim.x);
   stage_tile<T, HD>(dOs, (const T*)a.ctx + (int64_t)b * Sq * a.ldc + h * HD, a.ldc, Sq, qrows, blockDim.x);
+  __shared__ uint8_t smask[64];
+  if (a.mask != nullptr && threadIdx.x < Sk) smask[threadIdx.x] = a.mask[(int64_t)b * Sk + threadIdx.x];
   for (int e = threadIdx.x; e < 3 * HD; e += blockDim.x) bg[e] = 0.f;
   // zero the score tiles so that padded rows / keys read as exact zeros in phase 2
   for (int e = threadIdx.x; e < 64 * PP / 2; e += blockDim.x) {
     reinterpret_cast<uint32_t*>(Ps)[e] = 0u;
     reinterpret_cast<uint32_t*>(dSs)[e] = 0u;
   }
+  stage_wait();
   __syncthreads();
   const int row0 = warp * 16;
   if (row0 < Sq) {
@@ -275,7 +289,7 @@ __global__ void __launch_bounds__(128) attn_tc_bwd_kernel(const AttnTcDev a) {
         }
       }
     }
-    softmax_frag(s, NT, Sk, a.mask ? a.mask + (int64_t)b * Sk : nullptr, a.qscale, lane);
+    softmax_frag(s, NT, Sk, a.mask ? smask : nullptr, a.qscale, lane);
     // dropout on P and dP, delta = sum_j P * dP, dS = P * (dP - delta)
     const uint64_t base = (uint64_t)blockIdx.x * Sq * Sk;
     float dl0 = 0.f, dl1 = 0.f;

@@ -212,7 +212,8 @@ constexpr int TSTAGE_BYTES = TA_BYTES + TB_BYTES;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TEPI_WARP_BYTES = 4096;     // per-warp staging slab: 32 rows x 128 B
 constexpr int TEPI_BYTES = TC_EPI_WARPS * TEPI_WARP_BYTES;
-constexpr int TC_SMEM_BYTES = TSTAGES * TSTAGE_BYTES + TEPI_BYTES + 128 /*barriers + TMEM slot*/;   // 229,504 B of the 232,448 B limit
+constexpr int TEPI_BIAS_BYTES = 2 * TBN * 4;   // per accumulator stage: the tile's 256 bias values (fast epilogue)
+constexpr int TC_SMEM_BYTES = TSTAGES * TSTAGE_BYTES + TEPI_BYTES + 128 /*barriers + TMEM slot*/ + TEPI_BIAS_BYTES;   // 231,552 B of the 232,448 B limit
 constexpr int TC_THREADS = 128 + 32 * TC_EPI_WARPS;
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -440,6 +441,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     const int quad = warp & 3;
     const int half = ew >> 2;
     float* st = epi_stage + ew * (TEPI_WARP_BYTES / 4);      // 32 x 32 fp32 slab (general path) / 32 x 128 B rows (fast path)
+    float* bias_tab = reinterpret_cast<float*>(smem_gen + TSTAGES * TSTAGE_BYTES + TEPI_BYTES + 128);
     const uint32_t st_addr = smem_u32(st);
     bool store_pending = false;
     const int sub = lane >> 4;               // row of the pair this half-warp handles
@@ -474,6 +476,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         // registers, writes the 16-bit row into the 128B-swizzled slab and one lane issues a TMA store of the
         // 32 x 64 block (rows >= M and columns >= N are clipped by the tensor map: no predicates anywhere).
         const int64_t m = m0 + lane;
+        // the tile's bias values for this warp's 128 columns, staged once per tile in a table indexed by the accumulator
+        // stage (the 4 warps of a column half write identical values; a warp is never more than one tile ahead of
+        // another because stage reuse needs all 8 arrivals on tmem_empty)
+        float* tab = bias_tab + as * TBN + half * 128;
+        {
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int nn = n0 + half * 128 + lane * 4;
+          if (bias != nullptr) {
+            if (nn + 0 < N) bv.x = __ldg(bias + nn + 0);
+            if (nn + 1 < N) bv.y = __ldg(bias + nn + 1);
+            if (nn + 2 < N) bv.z = __ldg(bias + nn + 2);
+            if (nn + 3 < N) bv.w = __ldg(bias + nn + 3);
+          }
+          *reinterpret_cast<float4*>(tab + lane * 4) = bv;
+          __syncwarp();
+        }
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           const int col0 = half * 128 + c * 64;
@@ -483,18 +501,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * TBN + col0);
           tmem_ld32_nowait(taddr, v);
           tmem_ld32_nowait(taddr + 32, v + 32);
-          float bl = 0.f, bh = 0.f;              // lane j holds bias[nb + j] and bias[nb + 32 + j]
-          if (bias != nullptr) {
-            if (nb + lane < N) bl = __ldg(bias + nb + lane);
-            if (nb + 32 + lane < N) bh = __ldg(bias + nb + 32 + lane);
-          }
           tmem_ld_wait();
           uint32_t pk[32];
           const uint64_t idx0 = (uint64_t)m * (uint64_t)N + (uint64_t)nb;     // even (N and nb are even)
 #pragma unroll
           for (int j = 0; j < 64; j += 2) {
-            float v0 = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, j < 32 ? bl : bh, j & 31);
-            float v1 = __uint_as_float(v[j + 1]) + __shfl_sync(0xffffffffu, j < 32 ? bl : bh, (j + 1) & 31);
+            const float2 bb = *reinterpret_cast<const float2*>(tab + c * 64 + j);   // warp-uniform address: smem broadcast
+            float v0 = __uint_as_float(v[j]) + bb.x;
+            float v1 = __uint_as_float(v[j + 1]) + bb.y;
             if (act == 1) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
             if (thresh != 0u) {
               const uint32_t h = drop_hash(dk0, dk1, (idx0 + j) >> 1);
