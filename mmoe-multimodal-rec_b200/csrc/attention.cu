@@ -183,6 +183,146 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const AttnDev a) 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Short sequences (S <= 4: the two-token sequences of EnhancedCrossFuse, model.py:496-499): one WARP per
+// (sample, head), lanes across head_dim, everything in registers, fp32 math for every dtype.  A block takes
+// 8 samples of one head so the bias-gradient column sums reduce in shared memory before touching global memory.
+// ------------------------------------------------------------------------------------------
+constexpr int SMALL_S = 4, SMALL_C = 4;   // S <= 4, head_dim <= 128
+
+template <typename T>
+__global__ void __launch_bounds__(256) attn_small_kernel(const AttnDev a, int bwd) {
+  __shared__ float red[8][3 * 128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * 8 + warp, h = blockIdx.y;
+  const int hd = a.hd, Sq = a.Sq, Sk = a.Sk;
+  const bool live = b < a.B;
+  float q[SMALL_S][SMALL_C], k[SMALL_S][SMALL_C], v[SMALL_S][SMALL_C], d_o[SMALL_S][SMALL_C];
+#pragma unroll
+  for (int i = 0; i < SMALL_S; ++i)
+#pragma unroll
+    for (int c = 0; c < SMALL_C; ++c) {
+      const int col = lane + 32 * c;
+      const bool okc = live && col < hd;
+      q[i][c] = (okc && i < Sq) ? to_f<T>(((const T*)a.q)[((int64_t)b * Sq + i) * a.ldq + h * hd + col]) : 0.f;
+      k[i][c] = (okc && i < Sk) ? to_f<T>(((const T*)a.k)[((int64_t)b * Sk + i) * a.ldk + h * hd + col]) : 0.f;
+      v[i][c] = (okc && i < Sk) ? to_f<T>(((const T*)a.v)[((int64_t)b * Sk + i) * a.ldv + h * hd + col]) : 0.f;
+      d_o[i][c] = (bwd && okc && i < Sq) ? to_f<T>(((const T*)a.ctx)[((int64_t)b * Sq + i) * a.ldc + h * hd + col]) : 0.f;
+    }
+  float p[SMALL_S][SMALL_S], pd[SMALL_S][SMALL_S];
+  const uint64_t base = ((uint64_t)b * a.H + h) * Sq * Sk;
+#pragma unroll
+  for (int i = 0; i < SMALL_S; ++i) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < SMALL_S; ++j) {
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < SMALL_C; ++c) acc = fmaf(q[i][c], k[j][c], acc);
+      acc = warp_sum(acc) * a.qscale;
+      if (j >= Sk || (live && a.mask != nullptr && a.mask[(int64_t)b * Sk + j])) acc = -INFINITY;
+      p[i][j] = acc;
+      mx = fmaxf(mx, acc);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < SMALL_S; ++j) { p[i][j] = expf(p[i][j] - mx); sum += p[i][j]; }   // all-masked row -> NaN, as torch
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int j = 0; j < SMALL_S; ++j) {
+      p[i][j] *= inv;
+      pd[i][j] = p[i][j];
+      if (a.thresh != 0) pd[i][j] = drop_keep(a.k0, a.k1, base + (uint64_t)i * Sk + j, a.thresh) ? p[i][j] * a.drop_scale : 0.f;
+    }
+  }
+  if (!bwd) {
+#pragma unroll
+    for (int i = 0; i < SMALL_S; ++i)
+#pragma unroll
+      for (int c = 0; c < SMALL_C; ++c) {
+        const int col = lane + 32 * c;
+        if (live && i < Sq && col < hd) {
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < SMALL_S; ++j) acc = fmaf(pd[i][j], v[j][c], acc);
+          ((T*)a.ctx)[((int64_t)b * Sq + i) * a.ldc + h * hd + col] = from_f<T>(acc);
+        }
+      }
+    return;
+  }
+  // backward
+  float ds[SMALL_S][SMALL_S];
+#pragma unroll
+  for (int i = 0; i < SMALL_S; ++i) {
+    float dp[SMALL_S], dl = 0.f;
+#pragma unroll
+    for (int j = 0; j < SMALL_S; ++j) {
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < SMALL_C; ++c) acc = fmaf(d_o[i][c], v[j][c], acc);
+      acc = warp_sum(acc);
+      if (a.thresh != 0) acc = drop_keep(a.k0, a.k1, base + (uint64_t)i * Sk + j, a.thresh) ? acc * a.drop_scale : 0.f;
+      dp[j] = acc;
+      dl += p[i][j] * acc;
+    }
+#pragma unroll
+    for (int j = 0; j < SMALL_S; ++j) ds[i][j] = (i < Sq && j < Sk) ? p[i][j] * (dp[j] - dl) * a.qscale : 0.f;
+  }
+  float sq[SMALL_C], sk[SMALL_C], sv[SMALL_C];
+#pragma unroll
+  for (int c = 0; c < SMALL_C; ++c) sq[c] = sk[c] = sv[c] = 0.f;
+#pragma unroll
+  for (int i = 0; i < SMALL_S; ++i)
+#pragma unroll
+    for (int c = 0; c < SMALL_C; ++c) {
+      const int col = lane + 32 * c;
+      if (!(live && col < hd)) continue;
+      if (i < Sq) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < SMALL_S; ++j) acc = fmaf(ds[i][j], k[j][c], acc);
+        const T o = from_f<T>(acc);
+        ((T*)a.dq)[((int64_t)b * Sq + i) * a.ldq + h * hd + col] = o;
+        sq[c] += to_f<T>(o);
+      }
+      if (i < Sk) {           // here i indexes a key
+        float ak = 0.f, av = 0.f;
+#pragma unroll
+        for (int r = 0; r < SMALL_S; ++r) { ak = fmaf(ds[r][i], q[r][c], ak); av = fmaf(pd[r][i], d_o[r][c], av); }
+        const T ok = from_f<T>(ak), ov = from_f<T>(av);
+        ((T*)a.dk)[((int64_t)b * Sk + i) * a.ldk + h * hd + col] = ok;
+        ((T*)a.dv)[((int64_t)b * Sk + i) * a.ldv + h * hd + col] = ov;
+        sk[c] += to_f<T>(ok); sv[c] += to_f<T>(ov);
+      }
+    }
+  if (a.bgq == nullptr && a.bgk == nullptr && a.bgv == nullptr) return;
+#pragma unroll
+  for (int c = 0; c < SMALL_C; ++c) {
+    const int col = lane + 32 * c;
+    red[warp][col] = sq[c]; red[warp][128 + col] = sk[c]; red[warp][256 + col] = sv[c];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 3 * 128; e += 256) {
+    const int which = e >> 7, col = e & 127;
+    if (col >= hd) continue;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][e];
+    float* dst = which == 0 ? a.bgq : (which == 1 ? a.bgk : a.bgv);
+    if (dst != nullptr) atomicAdd(dst + h * hd + col, t);
+  }
+}
+
+template <typename T>
+static int launch_small(const AttnDev& d, int bwd, cudaStream_t s) {
+  dim3 grid((unsigned)((d.B + 7) / 8), (unsigned)d.H);
+  attn_small_kernel<T><<<grid, 256, 0, s>>>(d, bwd);
+  MMOE_LAUNCH_OK("attn_small_kernel");
+  return 0;
+}
+static bool small_ok(const AttnArgs& a) { return a.Sq <= SMALL_S && a.Sk <= SMALL_S && a.hd <= 32 * SMALL_C; }
+
 static int fill(AttnDev* d, const AttnArgs& a) {
   MMOE_CHECK(a.Sq >= 1 && a.Sq <= 64 && a.Sk >= 1 && a.Sk <= 64, "attention: sequence lengths must be in [1,64] (got %d,%d)", a.Sq, a.Sk);
   MMOE_CHECK(a.hd >= 1 && a.hd <= 128, "attention: head_dim must be <= 128 (got %d)", a.hd);
@@ -229,6 +369,13 @@ static bool force_exact() {
 
 int attention_fwd(const AttnArgs& a, cudaStream_t s) {
   if (a.B == 0) return 0;
+  if (small_ok(a)) {
+    AttnDev d;
+    MMOE_TRY(fill(&d, a));
+    if (a.dtype == MMOE_BF16) return launch_small<__nv_bfloat16>(d, 0, s);
+    if (a.dtype == MMOE_F16) return launch_small<__half>(d, 0, s);
+    return launch_small<float>(d, 0, s);
+  }
   if (!force_exact() && attention_tc_supported(a)) return attention_tc(a, false, s);
   AttnDev d;
   MMOE_TRY(fill(&d, a));
@@ -238,6 +385,13 @@ int attention_fwd(const AttnArgs& a, cudaStream_t s) {
 }
 int attention_bwd(const AttnArgs& a, cudaStream_t s) {
   if (a.B == 0) return 0;
+  if (small_ok(a)) {
+    AttnDev d;
+    MMOE_TRY(fill(&d, a));
+    if (a.dtype == MMOE_BF16) return launch_small<__nv_bfloat16>(d, 1, s);
+    if (a.dtype == MMOE_F16) return launch_small<__half>(d, 1, s);
+    return launch_small<float>(d, 1, s);
+  }
   if (!force_exact() && attention_tc_supported(a)) return attention_tc(a, true, s);
   AttnDev d;
   MMOE_TRY(fill(&d, a));

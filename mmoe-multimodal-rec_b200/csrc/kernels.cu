@@ -80,13 +80,13 @@ int cast_f32(const float* x, void* y, int64_t n, int dtype, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------- cast + dropout + column sums
-// block = 256 threads, owns a panel of 32 rows; thread t owns 4 columns (c = 4t + 1024*j)
+// block = 256 threads, owns a panel of `rpb` rows x 1024 columns (blockIdx.y); thread t owns 4 adjacent columns
 template <typename T>
 __global__ void cast_drop_colsum_kernel(const float* __restrict__ x, T* __restrict__ g, float* __restrict__ colsum,
-                                        int64_t rows, int cols, uint32_t thresh, float scale, uint32_t k0, uint32_t k1) {
-  const int64_t r0 = (int64_t)blockIdx.x * 32;
-  const int64_t r1 = min(rows, r0 + 32);
-  for (int c = threadIdx.x * 4; c < cols; c += blockDim.x * 4) {
+                                        int64_t rows, int cols, uint32_t thresh, float scale, uint32_t k0, uint32_t k1, int rpb) {
+  const int64_t r0 = (int64_t)blockIdx.x * rpb;
+  const int64_t r1 = min(rows, r0 + rpb);
+  for (int c = blockIdx.y * 1024 + threadIdx.x * 4; c < min(cols, (int)(blockIdx.y + 1) * 1024); c += 1024) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int64_t r = r0; r < r1; ++r) {
       float4 v = load4<float>(x + r * cols + c);
@@ -112,16 +112,27 @@ __global__ void cast_drop_colsum_kernel(const float* __restrict__ x, T* __restri
   }
 }
 
+// rows per block of the column-owning panel kernels: tall panels amortise the column-sum atomics, but the grid must
+// still cover the chip a few times over (small-batch modules would otherwise run on a handful of SMs)
+static int panel_rows(int64_t rows, int cols) {
+  const int64_t col_chunks = (cols + 1023) / 1024;
+  int64_t rpb = rows * col_chunks / ((int64_t)sm_count() * 4);
+  if (rpb > 64) rpb = 64;
+  if (rpb < 2) rpb = 2;
+  return (int)rpb;
+}
+
 int cast_drop_colsum(const float* x, void* g, float* colsum, int64_t rows, int cols, float drop_p, uint32_t k0, uint32_t k1,
                      int dtype, cudaStream_t s) {
   if (rows == 0) return 0;
   MMOE_CHECK(cols % 4 == 0, "cast_drop_colsum: cols must be a multiple of 4");
   const uint32_t thresh = drop_p > 0.f ? drop_threshold(drop_p) : 0u;
   const float scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  const int blocks = (int)((rows + 31) / 32);
-  if (dtype == MMOE_BF16) cast_drop_colsum_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(x, (__nv_bfloat16*)g, colsum, rows, cols, thresh, scale, k0, k1);
-  else if (dtype == MMOE_F16) cast_drop_colsum_kernel<__half><<<blocks, 256, 0, s>>>(x, (__half*)g, colsum, rows, cols, thresh, scale, k0, k1);
-  else cast_drop_colsum_kernel<float><<<blocks, 256, 0, s>>>(x, (float*)g, colsum, rows, cols, thresh, scale, k0, k1);
+  const int rpb = panel_rows(rows, cols);
+  const dim3 grid((unsigned)((rows + rpb - 1) / rpb), (unsigned)((cols + 1023) / 1024));
+  if (dtype == MMOE_BF16) cast_drop_colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(x, (__nv_bfloat16*)g, colsum, rows, cols, thresh, scale, k0, k1, rpb);
+  else if (dtype == MMOE_F16) cast_drop_colsum_kernel<__half><<<grid, 256, 0, s>>>(x, (__half*)g, colsum, rows, cols, thresh, scale, k0, k1, rpb);
+  else cast_drop_colsum_kernel<float><<<grid, 256, 0, s>>>(x, (float*)g, colsum, rows, cols, thresh, scale, k0, k1, rpb);
   MMOE_LAUNCH_OK("cast_drop_colsum_kernel");
   return 0;
 }
@@ -267,12 +278,12 @@ int add_cast(const float* a, const void* b, float* out_f, void* out_t, int64_t n
 }
 
 // ---------------------------------------------------------------- ReLU(+dropout) backward mask + bias-gradient column sums
-// block = 256 threads, panel of 64 rows; a thread owns 4 adjacent columns
+// block = 256 threads, panel of `rpb` rows x 1024 columns (blockIdx.y); a thread owns 4 adjacent columns
 template <typename T>
 __global__ void __launch_bounds__(256) relu_mask_colsum_kernel(T* __restrict__ g, const T* __restrict__ h, float* __restrict__ colsum,
-                                                               int64_t rows, int cols, float scale) {
-  const int64_t r0 = (int64_t)blockIdx.x * 64, r1 = min(rows, r0 + 64);
-  for (int c = threadIdx.x * 4; c < cols; c += 256 * 4) {
+                                                               int64_t rows, int cols, float scale, int rpb) {
+  const int64_t r0 = (int64_t)blockIdx.x * rpb, r1 = min(rows, r0 + rpb);
+  for (int c = blockIdx.y * 1024 + threadIdx.x * 4; c < min(cols, (int)(blockIdx.y + 1) * 1024); c += 1024) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
     for (int64_t r = r0; r < r1; ++r) {
@@ -295,10 +306,11 @@ __global__ void __launch_bounds__(256) relu_mask_colsum_kernel(T* __restrict__ g
 int relu_mask_colsum(void* g, const void* h, float* colsum, int64_t rows, int cols, float scale, int dtype, cudaStream_t s) {
   if (rows == 0) return 0;
   MMOE_CHECK(cols % 4 == 0, "relu_mask_colsum: cols must be a multiple of 4");
-  const int blocks = (int)((rows + 63) / 64);
-  if (dtype == MMOE_BF16) relu_mask_colsum_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((__nv_bfloat16*)g, (const __nv_bfloat16*)h, colsum, rows, cols, scale);
-  else if (dtype == MMOE_F16) relu_mask_colsum_kernel<__half><<<blocks, 256, 0, s>>>((__half*)g, (const __half*)h, colsum, rows, cols, scale);
-  else relu_mask_colsum_kernel<float><<<blocks, 256, 0, s>>>((float*)g, (const float*)h, colsum, rows, cols, scale);
+  const int rpb = panel_rows(rows, cols);
+  const dim3 grid((unsigned)((rows + rpb - 1) / rpb), (unsigned)((cols + 1023) / 1024));
+  if (dtype == MMOE_BF16) relu_mask_colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((__nv_bfloat16*)g, (const __nv_bfloat16*)h, colsum, rows, cols, scale, rpb);
+  else if (dtype == MMOE_F16) relu_mask_colsum_kernel<__half><<<grid, 256, 0, s>>>((__half*)g, (const __half*)h, colsum, rows, cols, scale, rpb);
+  else relu_mask_colsum_kernel<float><<<grid, 256, 0, s>>>((float*)g, (const float*)h, colsum, rows, cols, scale, rpb);
   MMOE_LAUNCH_OK("relu_mask_colsum_kernel");
   return 0;
 }
@@ -311,12 +323,16 @@ struct LnBwdDev {
   int64_t rows; int d;
 };
 
-template <typename DT_, typename XT, typename T>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdDev a) {
-  __shared__ float red[8][LN_NV * 128];
+// NV = float4 per lane (6 covers d <= 768).  128-thread blocks, up to 3 per SM: the kernel is a stream of long-latency row
+// loads, so resident warps (not arithmetic) set its speed.
+template <typename DT_, typename XT, typename T, int NV>
+__global__ void __launch_bounds__(128, 3) ln_bwd_kernel(const LnBwdDev a) {
+  constexpr int LN_NV = NV;
+  constexpr int WARPS = 4;
+  __shared__ float red[WARPS][NV * 128];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t warp0 = (int64_t)blockIdx.x * 8 + wib;
-  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  const int64_t warp0 = (int64_t)blockIdx.x * WARPS + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * WARPS;
   const int d = a.d;
   const float inv_d = 1.0f / (float)d;
   float4 acc_g[LN_NV], acc_b[LN_NV], acc_c[LN_NV];
@@ -385,10 +401,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdDev a) {
       if (c < d) *reinterpret_cast<float4*>(&red[wib][c]) = acc[i];
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < d; c += 256) {
+    for (int c = threadIdx.x; c < d; c += 128) {
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) t += red[w][c];
+      for (int w = 0; w < WARPS; ++w) t += red[w][c];
       atomicAdd(dst + c, t);
     }
     __syncthreads();
@@ -397,14 +413,19 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdDev a) {
   if (a.g_colsum != nullptr) reduce_to(acc_c, a.g_colsum);
 }
 
-template <typename T>
-static int ln_bwd_dispatch(const LnBwdDev& dev, bool dy_f32, bool x_f32, int blocks, cudaStream_t s) {
-  if (dy_f32 && x_f32)       ln_bwd_kernel<float, float, T><<<blocks, 256, 0, s>>>(dev);
-  else if (dy_f32 && !x_f32) ln_bwd_kernel<float, T, T><<<blocks, 256, 0, s>>>(dev);
-  else if (!dy_f32 && x_f32) ln_bwd_kernel<T, float, T><<<blocks, 256, 0, s>>>(dev);
-  else                       ln_bwd_kernel<T, T, T><<<blocks, 256, 0, s>>>(dev);
+template <typename T, int NV>
+static int ln_bwd_dispatch_nv(const LnBwdDev& dev, bool dy_f32, bool x_f32, int blocks, cudaStream_t s) {
+  if (dy_f32 && x_f32)       ln_bwd_kernel<float, float, T, NV><<<blocks, 128, 0, s>>>(dev);
+  else if (dy_f32 && !x_f32) ln_bwd_kernel<float, T, T, NV><<<blocks, 128, 0, s>>>(dev);
+  else if (!dy_f32 && x_f32) ln_bwd_kernel<T, float, T, NV><<<blocks, 128, 0, s>>>(dev);
+  else                       ln_bwd_kernel<T, T, T, NV><<<blocks, 128, 0, s>>>(dev);
   MMOE_LAUNCH_OK("ln_bwd_kernel");
   return 0;
+}
+template <typename T>
+static int ln_bwd_dispatch(const LnBwdDev& dev, bool dy_f32, bool x_f32, int blocks, cudaStream_t s) {
+  if (dev.d <= 768) return ln_bwd_dispatch_nv<T, 6>(dev, dy_f32, x_f32, blocks, s);
+  return ln_bwd_dispatch_nv<T, 8>(dev, dy_f32, x_f32, blocks, s);
 }
 
 int layernorm_bwd(const LnBwdArgs& a, cudaStream_t s) {
@@ -417,8 +438,8 @@ int layernorm_bwd(const LnBwdArgs& a, cudaStream_t s) {
   dev.thresh = a.drop_p > 0.f ? drop_threshold(a.drop_p) : 0u;
   dev.scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
   dev.k0 = a.k0; dev.k1 = a.k1; dev.rows = a.rows; dev.d = a.d;
-  int64_t blocks = (a.rows + 7) / 8;
-  const int64_t cap = (int64_t)sm_count() * 2;
+  int64_t blocks = (a.rows + 3) / 4;
+  const int64_t cap = (int64_t)sm_count() * 6;
   if (blocks > cap) blocks = cap;
   MMOE_CHECK((a.dy_dtype == MMOE_F32 || a.dy_dtype == a.dtype) && (a.x_dtype == MMOE_F32 || a.x_dtype == a.dtype),
              "layernorm_bwd: dy and x must be fp32 or the operand dtype");
