@@ -249,7 +249,7 @@ def main():
         m.train(not args.eval_mode)
     if distributed:
         from torch.nn.parallel import DistributedDataParallel as DDP
-        cross_c, cui_c, cti_c, head_c = (DDP(m, device_ids=[local_rank]) for m in (cross, cui, cti, head))
+        cross_c, cui_c, cti_c, head_c = (DDP(m, device_ids=[local_rank], gradient_as_bucket_view=True) for m in (cross, cui, cti, head))
     else:
         cross_c, cui_c, cti_c, head_c = cross, cui, cti, head
     pw_g = torch.tensor(858627.0 / 990303.0, device=dev)      # train.py:189-192

@@ -185,6 +185,14 @@ int mmoe_cross_fwd(const mmoe_call* c, const mmoe_cross_cfg* cfg, const float* u
 int mmoe_cross_bwd(const mmoe_call* c, const mmoe_cross_cfg* cfg, const float* user, const uint8_t* user_mask,
                    const float* item, const uint8_t* item_mask, const float* dout, float* d_user, float* d_item);
 
+/* The same backward in stages, so that finished parameter gradients can be handed to DDP's bucketed all-reduce while
+ * later stages still run.  stage: -1 = everything; 0 = tail (MLP, LN, pooling, cross attention; leaves the stream
+ * gradients in the workspace); 100 + l = encoder layer l of the user stack; 200 + l = layer l of the item stack.
+ * Order: tail first, then each stack from its last layer down.  All stages of one backward share the workspace and the
+ * (zeroed) grads; d_user / d_item are written by the layer-0 stages. */
+int mmoe_cross_bwd_stage(const mmoe_call* c, const mmoe_cross_cfg* cfg, int stage, const float* user, const uint8_t* user_mask,
+                         const float* item, const uint8_t* item_mask, const float* dout, float* d_user, float* d_item);
+
 /* Layout query for tests/debugging: byte range inside the saved blob of an encoder layer's activation.
  * stream_id 0 = user stack, 1 = item stack; which 0 = FFN activation h [B*S,4d] T, 1 = layer output [B*S,d] fp32. */
 int mmoe_cross_saved_offset(const mmoe_cross_cfg* cfg, int32_t B, int dtype, int home, int stream_id, int layer, int which,

@@ -95,6 +95,7 @@ PROTOTYPES = {
     "mmoe_cross_workspace_bytes": (_sz, [_P(CrossCfg), _i32, C.c_int]),
     "mmoe_cross_fwd": (C.c_int, [_P(Call), _P(CrossCfg), _vp, _vp, _vp, _vp, _vp]),
     "mmoe_cross_bwd": (C.c_int, [_P(Call), _P(CrossCfg), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mmoe_cross_bwd_stage": (C.c_int, [_P(Call), _P(CrossCfg), C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mmoe_cross_saved_offset": (C.c_int, [_P(CrossCfg), _i32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P(_sz), _P(_sz)]),
     "mmoe_fuse_saved_offset": (C.c_int, [_P(FuseCfg), _i32, C.c_int, C.c_int, C.c_int, C.c_int, _P(_sz), _P(_sz)]),
     "mmoe_fuse_saved_bytes": (_sz, [_P(FuseCfg), _i32, C.c_int]),

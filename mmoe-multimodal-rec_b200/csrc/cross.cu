@@ -340,8 +340,12 @@ extern "C" int mmoe_cross_fwd(const mmoe_call* c, const mmoe_cross_cfg* cfg, con
   return 0;
 }
 
-extern "C" int mmoe_cross_bwd(const mmoe_call* c, const mmoe_cross_cfg* cfg, const float* user, const uint8_t* user_mask,
-                              const float* item, const uint8_t* item_mask, const float* dout, float* d_user, float* d_item) {
+// stage: -1 = whole backward; 0 = tail (MLP, LN, pooling, cross attention: leaves dU / dI in the workspace);
+// 100 + l = encoder layer l of the user stack; 200 + l = encoder layer l of the item stack.  Stages must run tail
+// first, then each stack from its last layer down; the same workspace (and zeroed grads) must be passed to all of them.
+// Splitting lets the caller hand finished parameter gradients to DDP's bucketed all-reduce while later stages still run.
+extern "C" int mmoe_cross_bwd_stage(const mmoe_call* c, const mmoe_cross_cfg* cfg, int stage, const float* user, const uint8_t* user_mask,
+                                    const float* item, const uint8_t* item_mask, const float* dout, float* d_user, float* d_item) {
   MMOE_TRY(check_cfg(cfg, c->B));
   if (c->B == 0) return 0;
   const int B = c->B, S = cfg->S, d = cfg->d, ff = 4 * d, dtype = c->dtype;
@@ -361,8 +365,9 @@ extern "C" int mmoe_cross_bwd(const mmoe_call* c, const mmoe_cross_cfg* cfg, con
   uint32_t k0, k1;
   const float* U = s.U;
 
+  const bool do_tail = stage == -1 || stage == 0;
   const float* dpooled = dout;
-  if (!c->home) {
+  if (do_tail && !c->home) {
     // out = normed + drop(h W2^T + b2)
     site_keys(c->seed, 103, &k0, &k1);
     MMOE_TRY(cast_drop_colsum(dout, t.g, (float*)G[ix.m3_b], B, d, drop_p, k0, k1, dtype, st));
@@ -390,6 +395,7 @@ extern "C" int mmoe_cross_bwd(const mmoe_call* c, const mmoe_cross_cfg* cfg, con
     }
     dpooled = t.dpooled;
   }
+  if (do_tail) {
   {
     PoolDev a{};
     a.U = U; a.C = s.c; a.gate = (const float*)P[ix.gate]; a.query = (const float*)P[ix.query]; a.mask = user_mask;
@@ -435,20 +441,29 @@ extern "C" int mmoe_cross_bwd(const mmoe_call* c, const mmoe_cross_cfg* cfg, con
         linear_wgrad(t.dkv, 2 * d, s.It, d, g_w_in + (size_t)d * d, M, 2 * d, d)};
     MMOE_TRY(gemm_grouped(p, 4, dtype, 0, st));
   }
+  }
   EncCtx ec{};
   ec.dtype = dtype; ec.M = M; ec.Bseq = B; ec.S = S; ec.d = d; ec.ff = ff; ec.H = cfg->n_head;
   ec.drop_p = drop_p; ec.seed = c->seed; ec.stream = st;
+  // item stack first: DDP reduces buckets in reverse registration order (mlp/cross_attn, self_item, self_user)
   for (int l = cfg->n_layer - 1; l >= 0; --l) {
-    ec.mask = user_mask; ec.site0 = 16 * l;
-    const float* x_in = l == 0 ? user : s.user[l].x_sum;
-    MMOE_TRY(enc_bwd(ec, enc_w(P + ix.user0 + 12 * l), enc_g(G + ix.user0 + 12 * l), x_in, s.user[l], t.enc, t.dU,
-                     l == 0 ? d_user : t.dU));
-  }
-  for (int l = cfg->n_layer - 1; l >= 0; --l) {
+    if (!(stage == -1 || stage == 200 + l)) continue;
     ec.mask = item_mask; ec.site0 = 16 * l + 8;
     const float* x_in = l == 0 ? item : s.item[l].x_sum;
     MMOE_TRY(enc_bwd(ec, enc_w(P + ix.item0 + 12 * l), enc_g(G + ix.item0 + 12 * l), x_in, s.item[l], t.enc, t.dI,
                      l == 0 ? d_item : t.dI));
   }
+  for (int l = cfg->n_layer - 1; l >= 0; --l) {
+    if (!(stage == -1 || stage == 100 + l)) continue;
+    ec.mask = user_mask; ec.site0 = 16 * l;
+    const float* x_in = l == 0 ? user : s.user[l].x_sum;
+    MMOE_TRY(enc_bwd(ec, enc_w(P + ix.user0 + 12 * l), enc_g(G + ix.user0 + 12 * l), x_in, s.user[l], t.enc, t.dU,
+                     l == 0 ? d_user : t.dU));
+  }
   return 0;
+}
+
+extern "C" int mmoe_cross_bwd(const mmoe_call* c, const mmoe_cross_cfg* cfg, const float* user, const uint8_t* user_mask,
+                              const float* item, const uint8_t* item_mask, const float* dout, float* d_user, float* d_item) {
+  return mmoe_cross_bwd_stage(c, cfg, -1, user, user_mask, item, item_mask, dout, d_user, d_item);
 }

@@ -231,6 +231,121 @@ class CrossFn(torch.autograd.Function):
         return (None, None, None, None, None, None, d_user.to(ctx.in_dtypes[0]), None, d_item.to(ctx.in_dtypes[1]), None, *grads)
 
 
+
+
+# ----------------------------------------------------------------------------------------------
+# RobustTextCrossExpert with a staged backward.
+# Forward is one library call (made by the tail stage); backward is split into autograd nodes — tail, then one per
+# encoder layer — so that each node's parameter gradients reach DDP's reducer as soon as that stage has been
+# enqueued and their bucketed all-reduce overlaps the stages still to come.  Nodes are created user stack first,
+# item stack second, tail last, hence run tail -> item layers -> user layers: DDP's bucket order.
+# ----------------------------------------------------------------------------------------------
+class _CrossRun:
+    """State shared by the stage nodes of one forward call."""
+    __slots__ = ("cfg", "home", "training", "drop_p", "seed", "dtype", "u", "um", "it", "im", "pt", "saved",
+                 "views", "gptrs", "work", "d_user", "d_item")
+
+
+def _cross_stage_call(run: "_CrossRun", stage: int, dout_ptr):
+    L = lib()
+    cfg = run.cfg
+    B = run.u.shape[0]
+    c = _call(run.dtype, B, run.training, run.home, run.drop_p, run.seed, run.pt, run.gptrs, run.saved, run.work)
+    check(L.mmoe_cross_bwd_stage(C.byref(c), C.byref(cfg), stage, run.u.data_ptr(), run.um.data_ptr(), run.it.data_ptr(),
+                                 run.im.data_ptr(), dout_ptr, run.d_user.data_ptr(), run.d_item.data_ptr()), "cross_bwd_stage")
+
+
+class CrossLayerStage(torch.autograd.Function):
+    """Autograd node of one encoder layer of the user (stage 100+l) or item (200+l) stack."""
+
+    @staticmethod
+    def forward(ctx, holder, stage: int, idx0: int, x, *layer_params):
+        ctx.holder, ctx.stage, ctx.idx0 = holder, stage, idx0
+        ctx.param_req = [p.requires_grad for p in layer_params]
+        ctx.is_first = (stage % 100) == 0
+        ctx.x_dtype = x.dtype
+        return x.new_empty(0)                      # token: only carries the graph edge to the next stage
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, _tok_grad):
+        run = ctx.holder[0]
+        _cross_stage_call(run, ctx.stage, None)
+        grads = [run.views[ctx.idx0 + i] if req else None for i, req in enumerate(ctx.param_req)]
+        if ctx.is_first:
+            dx = (run.d_user if ctx.stage < 200 else run.d_item).to(ctx.x_dtype)
+        else:
+            dx = _tok_grad.new_empty(0)
+        return (None, None, None, dx, *grads)
+
+
+class CrossTailStage(torch.autograd.Function):
+    """Runs the whole forward; its backward node covers MLP, LayerNorm, pooling, gate mix and the cross attention."""
+
+    @staticmethod
+    def forward(ctx, holder, pack: ParamPack, cfg: CrossCfg, home: bool, used, training: bool, drop_p: float, all_params,
+                tail_idx, user, user_mask, item, item_mask, tok_user, tok_item, *tail_params):
+        _require_cuda(user, user_mask, item, item_mask)
+        L = lib()
+        run = _CrossRun()
+        run.cfg, run.home, run.training, run.drop_p = cfg, home, training, drop_p
+        run.dtype = compute_dtype()
+        run.u, run.it = _f32c(user), _f32c(item)
+        run.um = user_mask.detach().to(torch.bool).contiguous().view(torch.uint8)
+        run.im = item_mask.detach().to(torch.bool).contiguous().view(torch.uint8)
+        B, dev = run.u.shape[0], run.u.device
+        run.pt = pack.tensors(all_params, run.dtype)
+        run.saved = _bytes(L.mmoe_cross_saved_bytes(C.byref(cfg), B, run.dtype), dev)
+        run.seed = _new_seed(training, drop_p)
+        run.views = run.gptrs = run.work = run.d_user = run.d_item = None
+        out = torch.empty((B, cfg.d), dtype=torch.float32, device=dev)
+        c = _call(run.dtype, B, training, home, drop_p, run.seed, run.pt, None, run.saved, None)
+        check(L.mmoe_cross_fwd(C.byref(c), C.byref(cfg), run.u.data_ptr(), run.um.data_ptr(), run.it.data_ptr(), run.im.data_ptr(),
+                               out.data_ptr()), "cross_fwd")
+        if DEBUG_SAVED is not None:
+            DEBUG_SAVED.append(("cross", cfg, home, B, run.dtype, run.saved))
+        holder.append(run)
+        ctx.holder, ctx.used, ctx.tail_idx = holder, list(used), list(tail_idx)
+        ctx.param_req = [p.requires_grad for p in tail_params]
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        run = ctx.holder[0]
+        L = lib()
+        B, dev = run.u.shape[0], run.u.device
+        run.views, run.gptrs = _alloc_grads(run.pt, ctx.used)
+        run.work = _bytes(L.mmoe_cross_workspace_bytes(C.byref(run.cfg), B, run.dtype), dev)
+        run.d_user, run.d_item = torch.empty_like(run.u), torch.empty_like(run.it)
+        do = _f32c(dout)
+        _cross_stage_call(run, 0, do.data_ptr())
+        grads = [run.views[i] if (req and run.views[i] is not None) else None for i, req in zip(ctx.tail_idx, ctx.param_req)]
+        empty = dout.new_empty(0)
+        return (None,) * 9 + (None, None, None, None, empty, empty, *grads)
+
+
+def cross_expert_staged(pack: ParamPack, cfg: CrossCfg, home: bool, used, training: bool, drop_p: float,
+                        user, user_mask, item, item_mask, params):
+    """Builds the stage chain for one forward call.  `params` in state_dict order:
+    [gate, self_user.0 (12) ..., self_item.0 (12) ..., cross_attn (4), pool.query, norm (2), mlp (4)]."""
+    n = cfg.n_layer
+    holder = []
+    tok_u = user
+    for l in range(n):
+        i0 = 1 + 12 * l
+        tok_u = CrossLayerStage.apply(holder, 100 + l, i0, tok_u, *params[i0:i0 + 12])
+    tok_i = item
+    for l in range(n):
+        i0 = 1 + 12 * n + 12 * l
+        tok_i = CrossLayerStage.apply(holder, 200 + l, i0, tok_i, *params[i0:i0 + 12])
+    tail_idx = [0] + list(range(1 + 24 * n, len(params)))
+    # unused HoME parameters (norm / mlp) are left out of the node so that their .grad stays None
+    tail_idx = [i for i in tail_idx if used[i]]
+    return CrossTailStage.apply(holder, pack, cfg, home, used, training, drop_p, list(params), tail_idx,
+                                user, user_mask, item, item_mask, tok_u, tok_i, *[params[i] for i in tail_idx])
+
+
 # ----------------------------------------------------------------------------------------------
 # EnhancedCrossFuse
 # ----------------------------------------------------------------------------------------------

@@ -102,6 +102,9 @@ class RobustTextCrossExpert(_Native):
         used = self._used(pack.names)
 
         def run(u, um, i, im):
+            if torch.is_grad_enabled():
+                # staged backward: parameter gradients become available layer by layer (DDP overlap)
+                return Fn.cross_expert_staged(pack, cfg, self._home, used, self.training, self._drop_p, u, um, i, im, params)
             return Fn.CrossFn.apply(pack, cfg, self._home, used, self.training, self._drop_p, u, um, i, im, *params)
 
         if not torch.is_grad_enabled() and B > NO_GRAD_CHUNK:
