@@ -89,43 +89,59 @@ class Passthrough(torch.nn.Module):
 # clocks sampler (nvidia-smi during the timed region)
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons sampled DURING the timed region through NVML (in-process thread, 20 ms period;
+    `nvidia-smi -lms` as a subprocess measurably disturbs a 200 ms timed region, NVML calls do not)."""
 
     def __init__(self, index: int):
         self.index = index
         self.samples = []
-        self.proc = None
+        self._stop = threading.Event()
+        self._thr = None
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may remap indices: resolve through the PCI bus id of the torch device
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index) if bus is None else pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self._h = None
+
+    def _loop(self):
+        nv, h = self._nv, self._h
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((sm, mx, rs))
+            except Exception:
+                pass
+            self._stop.wait(0.02)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append(line.strip())
+        if self._h is None:
+            return
+        self._thr = threading.Thread(target=self._loop, daemon=True)
+        self._thr.start()
 
     def stop(self):
-        if self.proc is not None:
-            time.sleep(0.15)
-            self.proc.terminate()
-        sm, mx, reasons = [], 0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            parts = [p.strip() for p in s.split(",")]
-            try:
-                sm.append(float(parts[0])); mx = max(mx, float(parts[1]))
-                for n, v in zip(names, parts[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                continue
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        nv = self._nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = sorted(n for n, bit in names.items() if any(s[2] & bit for s in self.samples))
+        return {"sm_mhz": float(sm[len(sm) // 2]), "sm_max_mhz": float(max(s[1] for s in self.samples)), "reasons": reasons,
+                "samples": len(sm)}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -205,7 +221,7 @@ def workload_config(B, n_gpus):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=512, help="per-GPU batch (train.py default 512)")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
@@ -233,6 +249,7 @@ def main():
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     L = pkg.lib()
     check(L.mmoe_init(), "init")
