@@ -229,6 +229,7 @@ def main():
     ap.add_argument("--cpu-baseline-batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eval-mode", action="store_true", help="dropout off (debug)")
+    ap.add_argument("--nccl-ctas", type=int, default=8, help="N>1: NCCL_MAX_CTAS and SMs the GEMM leaves to NCCL")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -250,9 +251,14 @@ def main():
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line
+        # ~280 MB of gradients per step overlap ~8 ms of backward: a few NCCL CTAs are plenty, and every SM NCCL holds
+        # is an SM the persistent GEMM cannot use while it runs
+        os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_ctas))
         dist.init_process_group("nccl", device_id=dev)
     L = pkg.lib()
     check(L.mmoe_init(), "init")
+    if distributed:
+        L.mmoe_set_sm_reserve(args.nccl_ctas)
 
     M = pkg.modules
     torch.manual_seed(1234)

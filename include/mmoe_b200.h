@@ -107,6 +107,11 @@ int mmoe_gemm_grouped(const mmoe_gemm_problem* problems /*host*/, int n_problems
 int mmoe_gemm_timing(int enable);
 int mmoe_gemm_timing_read(double* total_ms, double* total_flops, int64_t* launches, int tc_only);
 
+/* Number of SMs the persistent GEMM leaves free (its CTAs own a whole SM each and cannot co-reside with a running
+ * NCCL kernel).  Set it to the number of NCCL CTAs when gradient all-reduce overlaps backward; default 0 or the
+ * environment variable MMOE_SM_RESERVE. */
+int mmoe_set_sm_reserve(int n_sms);
+
 /* keep-mask a kernel would use for flat element index i in [0,n): out[i] = 1/0 (uint8). */
 int mmoe_dropout_mask(uint32_t key0, uint32_t key1, float p, int64_t n, uint8_t* out, void* stream);
 

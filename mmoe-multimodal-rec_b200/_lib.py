@@ -79,6 +79,7 @@ PROTOTYPES = {
     "mmoe_gemm_grouped": (C.c_int, [_P(GemmProblem), C.c_int, C.c_int, C.c_int, _vp]),
     "mmoe_gemm_timing": (C.c_int, [C.c_int]),
     "mmoe_gemm_timing_read": (C.c_int, [_P(C.c_double), _P(C.c_double), _P(_i64), C.c_int]),
+    "mmoe_set_sm_reserve": (C.c_int, [C.c_int]),
     "mmoe_dropout_mask": (C.c_int, [_u32, _u32, _f, _i64, _vp, _vp]),
     "mmoe_layernorm_fwd": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _i64, _i32, C.c_int, _vp]),
     "mmoe_attention_fwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32,

@@ -129,8 +129,8 @@ __device__ __forceinline__ void softmax_frag(float (&s)[8][4], int NT, int Sk, c
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         // a fully padded row gives exp(-inf - -inf) = NaN, as torch's softmax does
-        s[nt][e] = expf(s[nt][e] - mx0); sum0 += s[nt][e];
-        s[nt][2 + e] = expf(s[nt][2 + e] - mx1); sum1 += s[nt][2 + e];
+        s[nt][e] = __expf(s[nt][e] - mx0); sum0 += s[nt][e];          // ex2.approx path: 16-bit operands downstream
+        s[nt][2 + e] = __expf(s[nt][2 + e] - mx1); sum1 += s[nt][2 + e];
       }
     }
   }
@@ -183,15 +183,25 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcDev a) {
   }
   softmax_frag(s, NT, Sk, a.mask ? smask : nullptr, a.qscale, lane);
   if (a.thresh != 0) {
+    // element (row, key) has flat index base + row*Sk + key; keys 2t, 2t+1 share one hash when Sk is even
     const uint64_t base = (uint64_t)blockIdx.x * Sq * Sk;
+    const bool paired = (Sk & 1) == 0;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       if (nt < NT) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int row = row0 + g + (e >> 1) * 8, key = nt * 8 + 2 * t + (e & 1);
-          const bool keep = row < Sq && key < Sk && drop_keep(a.k0, a.k1, base + (uint64_t)row * Sk + key, a.thresh);
-          s[nt][e] = keep ? s[nt][e] * a.drop_scale : 0.f;
+        for (int hrow = 0; hrow < 2; ++hrow) {
+          const int row = row0 + g + hrow * 8, key = nt * 8 + 2 * t;
+          const uint64_t idx = base + (uint64_t)row * Sk + key;
+          bool k0, k1;
+          if (paired) {
+            const uint32_t hsh = drop_hash(a.k0, a.k1, idx >> 1);
+            k0 = (hsh & 0xFFFFu) >= a.thresh; k1 = (hsh >> 16) >= a.thresh;
+          } else {
+            k0 = drop_keep(a.k0, a.k1, idx, a.thresh); k1 = drop_keep(a.k0, a.k1, idx + 1, a.thresh);
+          }
+          s[nt][2 * hrow] = k0 ? s[nt][2 * hrow] * a.drop_scale : 0.f;
+          s[nt][2 * hrow + 1] = k1 ? s[nt][2 * hrow + 1] * a.drop_scale : 0.f;
         }
       }
     }
@@ -294,19 +304,32 @@ __global__ void __launch_bounds__(128) attn_tc_bwd_kernel(const AttnTcDev a) {
     const uint64_t base = (uint64_t)blockIdx.x * Sq * Sk;
     float dl0 = 0.f, dl1 = 0.f;
     float pd[8][4];
+    const bool paired = (Sk & 1) == 0;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
+      bool keep[4] = {true, true, true, true};
+      if (nt < NT && a.thresh != 0) {
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+          const int row = row0 + g + hrow * 8, key = nt * 8 + 2 * t;
+          const uint64_t idx = base + (uint64_t)row * Sk + key;
+          if (paired) {
+            const uint32_t hsh = drop_hash(a.k0, a.k1, idx >> 1);
+            keep[2 * hrow] = (hsh & 0xFFFFu) >= a.thresh; keep[2 * hrow + 1] = (hsh >> 16) >= a.thresh;
+          } else {
+            keep[2 * hrow] = drop_keep(a.k0, a.k1, idx, a.thresh); keep[2 * hrow + 1] = drop_keep(a.k0, a.k1, idx + 1, a.thresh);
+          }
+        }
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         pd[nt][e] = 0.f;
         if (nt < NT) {
-          float p = s[nt][e], d = dp[nt][e];
-          float pdrop = p;
+          const float p = s[nt][e];
+          float d = dp[nt][e], pdrop = p;
           if (a.thresh != 0) {
-            const int row = row0 + g + (e >> 1) * 8, key = nt * 8 + 2 * t + (e & 1);
-            const bool keep = row < Sq && key < Sk && drop_keep(a.k0, a.k1, base + (uint64_t)row * Sk + key, a.thresh);
-            d = keep ? d * a.drop_scale : 0.f;
-            pdrop = keep ? p * a.drop_scale : 0.f;
+            d = keep[e] ? d * a.drop_scale : 0.f;
+            pdrop = keep[e] ? p * a.drop_scale : 0.f;
           }
           pd[nt][e] = pdrop;
           dp[nt][e] = d;

@@ -699,6 +699,7 @@ static int fill_epi(EpiDev* d, const mmoe_gemm_problem& pr, int dtype) {
   return 0;
 }
 
+extern std::atomic<int> g_sm_reserve;
 static int launch_tc(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream_t stream) {
   TcParams P{};
   P.n_groups = n;
@@ -740,7 +741,12 @@ static int launch_tc(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream_t
     MMOE_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attr_set = true;
   }
-  const int grid = tiles < sm_count() ? tiles : sm_count();
+  // The persistent CTAs take a whole SM each (231 KB of shared memory), so they cannot share an SM with a resident
+  // communication kernel: when NCCL runs concurrently (DDP overlap) leave it `g_sm_reserve` SMs instead of queueing
+  // behind it.
+  int avail = sm_count() - g_sm_reserve.load(std::memory_order_relaxed);
+  if (avail < 1) avail = 1;
+  const int grid = tiles < avail ? tiles : avail;
   gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(P);
   MMOE_LAUNCH_OK("gemm_tc_kernel");
   return 0;
@@ -786,6 +792,7 @@ static std::mutex g_time_mu;
 static std::vector<TimedLaunch> g_timed;
 static std::vector<cudaEvent_t> g_event_pool;
 static std::atomic<int> g_timing_on{0};
+std::atomic<int> g_sm_reserve{getenv("MMOE_SM_RESERVE") ? atoi(getenv("MMOE_SM_RESERVE")) : 0};
 
 static cudaEvent_t take_event() {
   cudaEvent_t e;
@@ -866,5 +873,11 @@ extern "C" int mmoe_gemm_timing_read(double* total_ms, double* total_flops, int6
   }
   g_timed.clear();
   *total_ms = ms; *total_flops = fl; *launches = n;
+  return 0;
+}
+
+// SMs the persistent GEMM leaves free for concurrently running communication kernels (default 0, or env MMOE_SM_RESERVE).
+extern "C" int mmoe_set_sm_reserve(int n_sms) {
+  mmoe::g_sm_reserve.store(n_sms < 0 ? 0 : n_sms);
   return 0;
 }
