@@ -229,7 +229,9 @@ def main():
     ap.add_argument("--cpu-baseline-batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eval-mode", action="store_true", help="dropout off (debug)")
-    ap.add_argument("--nccl-ctas", type=int, default=8, help="N>1: NCCL_MAX_CTAS and SMs the GEMM leaves to NCCL")
+    ap.add_argument("--nccl-ctas", type=int, default=0,
+                    help="N>1: if > 0, cap NCCL at this many CTAs and keep as many SMs free of GEMM CTAs (measured: capping "
+                         "lengthens the exposed part of the all-reduce at N=2; default leaves NCCL alone)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -253,11 +255,12 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line
         # ~280 MB of gradients per step overlap ~8 ms of backward: a few NCCL CTAs are plenty, and every SM NCCL holds
         # is an SM the persistent GEMM cannot use while it runs
-        os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_ctas))
+        if args.nccl_ctas > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_ctas))
         dist.init_process_group("nccl", device_id=dev)
     L = pkg.lib()
     check(L.mmoe_init(), "init")
-    if distributed:
+    if distributed and args.nccl_ctas > 0:
         L.mmoe_set_sm_reserve(args.nccl_ctas)
 
     M = pkg.modules

@@ -90,6 +90,7 @@ struct alignas(64) TcParams {
   int n_groups;
   int total_tiles;
   int fmt;  // 0 f16, 1 bf16
+  int bn;   // tile width of this launch: 256, or 128 / 64 when 256-wide tiles would leave most SMs idle
 };
 
 struct SimtGroup {
@@ -373,10 +374,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileInfo t = decode_tile(p, tile);
         const TcGroup& g = p.g[t.gi];
-        const int m0 = t.m_blk * TBM, n0 = t.n_blk * TBN;
+        const int m0 = t.m_blk * TBM, n0 = t.n_blk * p.bn;
+        const uint32_t stage_tx = (uint32_t)(TA_BYTES + p.bn * TBK * 2);
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), TSTAGE_BYTES);
+          mbar_expect_tx(full_bar(stage), stage_tx);
           const uint32_t sa = smem_a0 + stage * TA_BYTES, sb = smem_b0 + stage * TB_BYTES;
           const int k0 = kb * TBK;
           if (g.a_major == 0) {
@@ -387,10 +389,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
               tma_load_2d(sa + j * (TBK * 128), &g.tma_a, full_bar(stage), m0 + j * 64, k0);
           }
           if (g.b_major == 0) {
-            tma_load_2d(sb, &g.tma_b, full_bar(stage), k0, n0);                 // box {64 k, 256 n}
+            tma_load_2d(sb, &g.tma_b, full_bar(stage), k0, n0);                 // box {64 k, bn n}
           } else {
 #pragma unroll
-            for (int j = 0; j < TBN / 64; ++j)                                  // boxes {64 n, 64 k}
+            for (int j = 0; j < p.bn / 64; ++j)                                 // boxes {64 n, 64 k}
               tma_load_2d(sb + j * (TBK * 128), &g.tma_b, full_bar(stage), n0 + j * 64, k0);
           }
           if (++stage == TSTAGES) { stage = 0; phase ^= 1u; }
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         // instruction descriptor: D fp32, A/B f16|bf16, majors, N>>3, M>>4
         const uint32_t idesc = (1u << 4) | ((uint32_t)p.fmt << 7) | ((uint32_t)p.fmt << 10) |
                                ((uint32_t)g.a_major << 15) | ((uint32_t)g.b_major << 16) |
-                               ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+                               ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * TBN);
@@ -451,7 +453,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const TileInfo t = decode_tile(p, tile);
       const TcGroup& g = p.g[t.gi];
       const EpiDev& E = g.epi;
-      const int m0 = t.m_blk * TBM + quad * 32, n0 = t.n_blk * TBN;
+      const int m0 = t.m_blk * TBM + quad * 32, n0 = t.n_blk * p.bn;
       const bool first = (t.split == 0);
       const int N = g.N;
       const int rows = min(32, g.M - m0);    // may be <= 0 for a ragged last tile
@@ -496,7 +498,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         for (int c = 0; c < 2; ++c) {
           const int col0 = half * 128 + c * 64;
           const int nb = n0 + col0;
-          if (nb >= N) break;
+          if (nb >= N || col0 >= p.bn) break;
           uint32_t v[64];
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * TBN + col0);
           tmem_ld32_nowait(taddr, v);
@@ -550,7 +552,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       for (int c = 0; c < 4; ++c) {
         const int col0 = half * 128 + c * 32;
         const int nb = n0 + col0;
-        if (nb >= N) break;
+        if (nb >= N || col0 >= p.bn) break;
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * TBN + col0), v);
         if (rows <= 0) continue;
@@ -704,6 +706,27 @@ static int launch_tc(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream_t
   TcParams P{};
   P.n_groups = n;
   P.fmt = dtype == MMOE_BF16 ? 1 : 0;
+  // tile width: small-batch problems (fuse experts, heads) are latency-bound single-wave launches; narrower tiles put
+  // more SMs on them and shorten the per-tile MMA chain (N = 64 costs a quarter of the cycles of N = 256 per K step)
+  int bn = TBN;
+  {
+    auto count_tiles = [&](int w) {
+      long t = 0;
+      for (int i = 0; i < n; ++i) {
+        const int kb = (pr[i].K + TBK - 1) / TBK;
+        int ks = pr[i].k_splits < 1 ? 1 : pr[i].k_splits;
+        if (ks > kb) ks = kb;
+        t += (long)((pr[i].M + TBM - 1) / TBM) * ((pr[i].N + w - 1) / w) * ks;
+      }
+      return t;
+    };
+    static const int forced = getenv("MMOE_DEBUG_BN") ? atoi(getenv("MMOE_DEBUG_BN")) : 0;
+    if (forced == 64 || forced == 128 || forced == 256) bn = forced;
+    else {
+      while (bn > 64 && count_tiles(bn) < sm_count()) bn >>= 1;
+    }
+  }
+  P.bn = bn;
   int tiles = 0;
   for (int i = 0; i < n; ++i) {
     TcGroup& g = P.g[i];
@@ -712,7 +735,7 @@ static int launch_tc(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream_t
     g.a_major = q.a_major; g.b_major = q.b_major;
     if (q.a_major == 0) MMOE_TRY(make_tmap(&g.tma_a, q.a, dtype, q.M, q.K, q.lda, TBM));
     else                MMOE_TRY(make_tmap(&g.tma_a, q.a, dtype, q.K, q.M, q.lda, TBK));
-    if (q.b_major == 0) MMOE_TRY(make_tmap(&g.tma_b, q.b, dtype, q.N, q.K, q.ldb, TBN));
+    if (q.b_major == 0) MMOE_TRY(make_tmap(&g.tma_b, q.b, dtype, q.N, q.K, q.ldb, bn));
     else                MMOE_TRY(make_tmap(&g.tma_b, q.b, dtype, q.K, q.N, q.ldb, TBK));
     MMOE_TRY(fill_epi(&g.epi, q, dtype));
     {
@@ -725,7 +748,7 @@ static int launch_tc(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream_t
       if (fast) MMOE_TRY(make_tmap(&g.tma_out, e.out, dtype, q.M, q.N, e.ldo, 32));
     }
     g.tiles_m = (q.M + TBM - 1) / TBM;
-    g.tiles_n = (q.N + TBN - 1) / TBN;
+    g.tiles_n = (q.N + bn - 1) / bn;
     g.kb_total = (q.K + TBK - 1) / TBK;
     int ks = q.k_splits < 1 ? 1 : q.k_splits;
     if (ks > g.kb_total) ks = g.kb_total;
