@@ -320,8 +320,10 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
+    t_host = time.perf_counter()
     for _ in range(args.steps):
         loss = step(resident)
+    host_ms_step = (time.perf_counter() - t_host) * 1e3 / args.steps     # time the host needs to ENQUEUE a step
     ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -397,6 +399,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(host[0]), "d2h_bytes_per_step": 4,
                     "note": "pinned host batch copied on a side stream (double buffered) every step; loss.item() read back every step"},
             "gpu_launches": launches,
+            "host_enqueue_ms_per_step": host_ms_step,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 grouped GEMM, all launches of the timed region)",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,

@@ -11,7 +11,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmmoe_b200.so")
+# MMOE_B200_LIB: A/B-test another build of the same ABI (developer switch; the default is the in-tree library)
+LIB_PATH = os.environ.get("MMOE_B200_LIB") or os.path.join(_HERE, "libmmoe_b200.so")
 
 F32, BF16, F16 = 0, 1, 2
 

@@ -78,6 +78,7 @@ struct alignas(64) TcGroup {
   CUtensorMap tma_a;
   CUtensorMap tma_b;
   CUtensorMap tma_out;   // kind 1 only: 16-bit output, box {64 cols, 32 rows}, 128B swizzle
+  CUtensorMap tma_pre;   // kind 1 with a pre-activation copy: same geometry
   EpiDev epi;
   int kind;              // 0 = general epilogue, 1 = fast 16-bit epilogue (bias, ReLU, dropout) through TMA store
   int M, N, K;
@@ -332,6 +333,10 @@ __device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int tile) {
   return t;
 }
 
+// BN: tile width (compile-time so the TMA issue loop and the instruction descriptor are constants — the pipeline is
+// latency-critical and a runtime width cost 5-14%).  RICH: the fast epilogue also handles GELU / sigmoid and a
+// pre-activation copy (kept out of the lean instantiation: the extra code slowed the ReLU/bias tiles by 15%).
+template <int BN, bool RICH>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   // SWIZZLE_128B tiles need 1024-byte alignment; the kernel has no static shared memory, so the dynamic window starts
   // at the (aligned) base of the CTA's shared memory.  Checked, not assumed.
@@ -374,8 +379,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileInfo t = decode_tile(p, tile);
         const TcGroup& g = p.g[t.gi];
-        const int m0 = t.m_blk * TBM, n0 = t.n_blk * p.bn;
-        const uint32_t stage_tx = (uint32_t)(TA_BYTES + p.bn * TBK * 2);
+        const int m0 = t.m_blk * TBM, n0 = t.n_blk * BN;
+        constexpr uint32_t stage_tx = (uint32_t)(TA_BYTES + BN * TBK * 2);
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), stage_tx);
@@ -392,7 +397,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
             tma_load_2d(sb, &g.tma_b, full_bar(stage), k0, n0);                 // box {64 k, bn n}
           } else {
 #pragma unroll
-            for (int j = 0; j < p.bn / 64; ++j)                                 // boxes {64 n, 64 k}
+            for (int j = 0; j < BN / 64; ++j)                                   // boxes {64 n, 64 k}
               tma_load_2d(sb + j * (TBK * 128), &g.tma_b, full_bar(stage), n0 + j * 64, k0);
           }
           if (++stage == TSTAGES) { stage = 0; phase ^= 1u; }
@@ -410,7 +415,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         // instruction descriptor: D fp32, A/B f16|bf16, majors, N>>3, M>>4
         const uint32_t idesc = (1u << 4) | ((uint32_t)p.fmt << 7) | ((uint32_t)p.fmt << 10) |
                                ((uint32_t)g.a_major << 15) | ((uint32_t)g.b_major << 16) |
-                               ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * TBN);
@@ -453,7 +458,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const TileInfo t = decode_tile(p, tile);
       const TcGroup& g = p.g[t.gi];
       const EpiDev& E = g.epi;
-      const int m0 = t.m_blk * TBM + quad * 32, n0 = t.n_blk * p.bn;
+      const int m0 = t.m_blk * TBM + quad * 32, n0 = t.n_blk * BN;
       const bool first = (t.split == 0);
       const int N = g.N;
       const int rows = min(32, g.M - m0);    // may be <= 0 for a ragged last tile
@@ -498,7 +503,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         for (int c = 0; c < 2; ++c) {
           const int col0 = half * 128 + c * 64;
           const int nb = n0 + col0;
-          if (nb >= N || col0 >= p.bn) break;
+          if (nb >= N || col0 >= BN) break;
           uint32_t v[64];
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * TBN + col0);
           tmem_ld32_nowait(taddr, v);
@@ -506,12 +511,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           tmem_ld_wait();
           uint32_t pk[32];
           const uint64_t idx0 = (uint64_t)m * (uint64_t)N + (uint64_t)nb;     // even (N and nb are even)
+          if (RICH && preact != nullptr) {
+            // pre-activation copy (for the backward of GELU): same slab, its own TMA store, before the activated tile
+#pragma unroll
+            for (int j = 0; j < 64; j += 2) {
+              const float2 bb = *reinterpret_cast<const float2*>(tab + c * 64 + j);
+              const float v0 = __uint_as_float(v[j]) + bb.x, v1 = __uint_as_float(v[j + 1]) + bb.y;
+              pk[j >> 1] = is_bf16 ? pack_bf16(v0, v1) : pack_f16(v0, v1);
+            }
+            if (store_pending) {
+              if (lane == 0) tma_store_wait_read();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const uint32_t dst = st_addr + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                           "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&g.tma_pre, st_addr, nb, m0);
+              tma_store_commit();
+            }
+            store_pending = true;
+          }
 #pragma unroll
           for (int j = 0; j < 64; j += 2) {
             const float2 bb = *reinterpret_cast<const float2*>(tab + c * 64 + j);   // warp-uniform address: smem broadcast
             float v0 = __uint_as_float(v[j]) + bb.x;
             float v1 = __uint_as_float(v[j + 1]) + bb.y;
             if (act == 1) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+            else if (RICH && act == 2) { v0 = gelu_f(v0); v1 = gelu_f(v1); }
+            else if (RICH && act == 3) { v0 = sigmoid_f(v0); v1 = sigmoid_f(v1); }
             if (thresh != 0u) {
               const uint32_t h = drop_hash(dk0, dk1, (idx0 + j) >> 1);
               v0 = ((h & 0xFFFFu) >= thresh) ? v0 * dscale : 0.f;
@@ -552,7 +585,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       for (int c = 0; c < 4; ++c) {
         const int col0 = half * 128 + c * 32;
         const int nb = n0 + col0;
-        if (nb >= N || col0 >= p.bn) break;
+        if (nb >= N || col0 >= BN) break;
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * TBN + col0), v);
         if (rows <= 0) continue;
@@ -728,6 +761,7 @@ static int launch_tc(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream_t
   }
   P.bn = bn;
   int tiles = 0;
+  bool rich = false;
   for (int i = 0; i < n; ++i) {
     TcGroup& g = P.g[i];
     const mmoe_gemm_problem& q = pr[i];
@@ -740,12 +774,15 @@ static int launch_tc(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream_t
     MMOE_TRY(fill_epi(&g.epi, q, dtype));
     {
       const mmoe_epilogue& e = q.epi;
-      const bool fast = e.out != nullptr && e.out_dtype != MMOE_F32 && !e.accumulate && e.preact == nullptr && e.bwd_mode == 0 &&
-                        e.residual == nullptr && e.colsum == nullptr && (e.act == 0 || e.act == 1) && e.alpha == 1.0f &&
+      const bool fast = e.out != nullptr && e.out_dtype != MMOE_F32 && !e.accumulate && e.bwd_mode == 0 &&
+                        e.residual == nullptr && e.colsum == nullptr && e.act >= 0 && e.act <= 3 && e.alpha == 1.0f &&
                         (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 && (e.ldo % 8) == 0 && q.k_splits <= 1 &&
+                        (e.preact == nullptr || (reinterpret_cast<uintptr_t>(e.preact) & 15) == 0) &&
                         getenv("MMOE_DEBUG_GENERAL_EPILOGUE") == nullptr;
       g.kind = fast ? 1 : 0;
       if (fast) MMOE_TRY(make_tmap(&g.tma_out, e.out, dtype, q.M, q.N, e.ldo, 32));
+      if (fast && e.preact != nullptr) MMOE_TRY(make_tmap(&g.tma_pre, e.preact, dtype, q.M, q.N, e.ldo, 32));
+      if (fast && (e.preact != nullptr || e.act >= 2)) rich = true;
     }
     g.tiles_m = (q.M + TBM - 1) / TBM;
     g.tiles_n = (q.N + bn - 1) / bn;
@@ -759,9 +796,15 @@ static int launch_tc(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream_t
   }
   P.total_tiles = tiles;
   if (tiles == 0) return 0;
+  using TcKernel = void (*)(const TcParams);
+  static const TcKernel kernels[3][2] = {{gemm_tc_kernel<64, false>, gemm_tc_kernel<64, true>},
+                                         {gemm_tc_kernel<128, false>, gemm_tc_kernel<128, true>},
+                                         {gemm_tc_kernel<256, false>, gemm_tc_kernel<256, true>}};
   static bool attr_set = false;
   if (!attr_set) {
-    MMOE_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 2; ++j)
+        MMOE_CUDA(cudaFuncSetAttribute(kernels[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attr_set = true;
   }
   // The persistent CTAs take a whole SM each (231 KB of shared memory), so they cannot share an SM with a resident
@@ -770,7 +813,7 @@ static int launch_tc(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream_t
   int avail = sm_count() - g_sm_reserve.load(std::memory_order_relaxed);
   if (avail < 1) avail = 1;
   const int grid = tiles < avail ? tiles : avail;
-  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(P);
+  kernels[bn == 64 ? 0 : (bn == 128 ? 1 : 2)][rich ? 1 : 0]<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(P);
   MMOE_LAUNCH_OK("gemm_tc_kernel");
   return 0;
 }

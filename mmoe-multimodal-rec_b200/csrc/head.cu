@@ -68,21 +68,267 @@ static HeadIdx head_idx() {
   return i;
 }
 
-struct HeadSaved { float *fused, *query, *w, *st; void *xn, *z1, *a1, *z2, *a2; };
+// ------------------------------------------------------------------------------------------
+// Fused head kernels (TwoTaskMMoE, model.py:562-577).  One warp per sample, float4 lanes, warp-shuffle reductions.
+//   forward : expert_vecs is read from HBM ONCE: mean query -> 2 gate GEMVs -> 2 softmaxes -> 2 weighted expert sums ->
+//             2 tower LayerNorms; only the normalised 16-bit tower inputs (3 KB/sample), the query and a few scalars
+//             are written.  Nothing fp32 of size [B,768] is materialised.
+//   backward: LayerNorm backward of both towers, gate-weight / softmax backward, query backward and the expert-vector
+//             gradient in one pass: reads d(xn) and expert_vecs, writes d(expert_vecs).
+// Algorithmic bytes per sample: forward 18.4 KB in + 3 KB out; backward 18.4 + 3 KB in, 18.4 KB out.
+// ------------------------------------------------------------------------------------------
+struct HeadFusedDev {
+  const float* ev; const float* wg[2]; const float* bg[2]; const float* ln_w[2]; const float* ln_b[2];
+  void* query_t; float* w; float* stats; void* xn;
+  const void* dxn; float* dl; float* d_ev; float* dgamma[2]; float* dbeta[2];
+  int64_t B; int d, n;
+};
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(256) head_mix_ln_fwd_kernel(const HeadFusedDev a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int d = a.d, n = a.n;
+  const float inv_d = 1.f / (float)d, inv_n = 1.f / (float)n;
+  for (int64_t b = warp0; b < a.B; b += nw) {
+    const float* evb = a.ev + b * (int64_t)n * d;
+    float4 q[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) q[i] = make_float4(0, 0, 0, 0);
+    for (int k = 0; k < n; ++k) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < d) { const float4 v = ld4(evb + k * d + c); q[i].x += v.x; q[i].y += v.y; q[i].z += v.z; q[i].w += v.w; }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      q[i].x *= inv_n; q[i].y *= inv_n; q[i].z *= inv_n; q[i].w *= inv_n;
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) {
+        T* qo = (T*)a.query_t + b * d + c;
+        qo[0] = from_f<T>(q[i].x); qo[1] = from_f<T>(q[i].y); qo[2] = from_f<T>(q[i].z); qo[3] = from_f<T>(q[i].w);
+      }
+    }
+    for (int t = 0; t < 2; ++t) {
+      float wk[MIX_MAXN];
+      float m = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < MIX_MAXN; ++k) {
+        wk[k] = -INFINITY;
+        if (k < n) {
+          float acc = 0.f;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < d) { const float4 w = ld4(a.wg[t] + k * d + c); acc += q[i].x * w.x + q[i].y * w.y + q[i].z * w.z + q[i].w * w.w; }
+          }
+          wk[k] = warp_sum(acc) + a.bg[t][k];
+          m = fmaxf(m, wk[k]);
+        }
+      }
+      float ssum = 0.f;
+#pragma unroll
+      for (int k = 0; k < MIX_MAXN; ++k) { wk[k] = k < n ? expf(wk[k] - m) : 0.f; ssum += wk[k]; }
+      const float inv = 1.f / ssum;
+      float4 f[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) f[i] = make_float4(0, 0, 0, 0);
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < MIX_MAXN; ++k) {
+        if (k < n) {
+          wk[k] *= inv;
+          if (lane == 0) a.w[((int64_t)t * a.B + b) * n + k] = wk[k];
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < d) { const float4 v = ld4(evb + k * d + c); f[i].x += wk[k] * v.x; f[i].y += wk[k] * v.y; f[i].z += wk[k] * v.z; f[i].w += wk[k] * v.w; }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) sum += f[i].x + f[i].y + f[i].z + f[i].w;      // lanes beyond d hold zeros
+      const float mean = warp_sum(sum) * inv_d;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < d) { const float x0 = f[i].x - mean, x1 = f[i].y - mean, x2 = f[i].z - mean, x3 = f[i].w - mean; sq += x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3; }
+      }
+      const float rstd = rsqrtf(warp_sum(sq) * inv_d + 1e-5f);
+      if (lane == 0) { a.stats[((int64_t)t * a.B + b) * 2] = mean; a.stats[((int64_t)t * a.B + b) * 2 + 1] = rstd; }
+      T* xo = (T*)a.xn + ((int64_t)t * a.B + b) * d;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < d) {
+          const float4 g = ld4(a.ln_w[t] + c), be = ld4(a.ln_b[t] + c);
+          xo[c + 0] = from_f<T>((f[i].x - mean) * rstd * g.x + be.x);
+          xo[c + 1] = from_f<T>((f[i].y - mean) * rstd * g.y + be.y);
+          xo[c + 2] = from_f<T>((f[i].z - mean) * rstd * g.z + be.z);
+          xo[c + 3] = from_f<T>((f[i].w - mean) * rstd * g.w + be.w);
+        }
+      }
+    }
+  }
+}
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(128, 2) head_ln_mix_bwd_kernel(const HeadFusedDev a) {
+  constexpr int WARPS = 4;
+  __shared__ float red[WARPS][NV * 128];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp0 = (int64_t)blockIdx.x * WARPS + wib, nw = (int64_t)gridDim.x * WARPS;
+  const int d = a.d, n = a.n;
+  const float inv_d = 1.f / (float)d, inv_n = 1.f / (float)n;
+  float4 acc_g[2][NV], acc_b[2][NV];
+#pragma unroll
+  for (int t = 0; t < 2; ++t)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc_g[t][i] = acc_b[t][i] = make_float4(0, 0, 0, 0);
+  for (int64_t b = warp0; b < a.B; b += nw) {
+    const float* evb = a.ev + b * (int64_t)n * d;
+    float4 df[2][NV], dq[NV];
+    float wt[2][MIX_MAXN];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) dq[i] = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+#pragma unroll
+      for (int k = 0; k < MIX_MAXN; ++k) wt[t][k] = k < n ? a.w[((int64_t)t * a.B + b) * n + k] : 0.f;
+      // fused_t = sum_k w_t[k] E_k  -> xhat
+      float4 f[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) f[i] = make_float4(0, 0, 0, 0);
+#pragma unroll
+      for (int k = 0; k < MIX_MAXN; ++k) {
+        if (k < n) {
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < d) { const float4 v = ld4(evb + k * d + c); f[i].x += wt[t][k] * v.x; f[i].y += wt[t][k] * v.y; f[i].z += wt[t][k] * v.z; f[i].w += wt[t][k] * v.w; }
+          }
+        }
+      }
+      const float mean = a.stats[((int64_t)t * a.B + b) * 2], rstd = a.stats[((int64_t)t * a.B + b) * 2 + 1];
+      const T* dy = (const T*)a.dxn + ((int64_t)t * a.B + b) * d;
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        df[t][i] = make_float4(0, 0, 0, 0);
+        if (c < d) {
+          const float4 g = ld4(a.ln_w[t] + c);
+          const float y0 = to_f<T>(dy[c]), y1 = to_f<T>(dy[c + 1]), y2 = to_f<T>(dy[c + 2]), y3 = to_f<T>(dy[c + 3]);
+          const float4 xh = make_float4((f[i].x - mean) * rstd, (f[i].y - mean) * rstd, (f[i].z - mean) * rstd, (f[i].w - mean) * rstd);
+          acc_g[t][i].x += y0 * xh.x; acc_g[t][i].y += y1 * xh.y; acc_g[t][i].z += y2 * xh.z; acc_g[t][i].w += y3 * xh.w;
+          acc_b[t][i].x += y0; acc_b[t][i].y += y1; acc_b[t][i].z += y2; acc_b[t][i].w += y3;
+          const float4 dg = make_float4(y0 * g.x, y1 * g.y, y2 * g.z, y3 * g.w);
+          s1 += dg.x + dg.y + dg.z + dg.w;
+          s2 += dg.x * xh.x + dg.y * xh.y + dg.z * xh.z + dg.w * xh.w;
+          df[t][i] = dg; f[i] = xh;          // keep dg in df, xhat in f until the row sums are known
+        }
+      }
+      s1 = warp_sum(s1) * inv_d; s2 = warp_sum(s2) * inv_d;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < d) {
+          df[t][i].x = rstd * (df[t][i].x - s1 - f[i].x * s2);
+          df[t][i].y = rstd * (df[t][i].y - s1 - f[i].y * s2);
+          df[t][i].z = rstd * (df[t][i].z - s1 - f[i].z * s2);
+          df[t][i].w = rstd * (df[t][i].w - s1 - f[i].w * s2);
+        }
+      }
+      // gate backward: dw_k = <dfused, E_k>; softmax' ; dq += dl_k Wg_k
+      float dw[MIX_MAXN], dot = 0.f;
+#pragma unroll
+      for (int k = 0; k < MIX_MAXN; ++k) {
+        dw[k] = 0.f;
+        if (k < n) {
+          float acc = 0.f;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < d) { const float4 v = ld4(evb + k * d + c); acc += df[t][i].x * v.x + df[t][i].y * v.y + df[t][i].z * v.z + df[t][i].w * v.w; }
+          }
+          dw[k] = warp_sum(acc);
+          dot += wt[t][k] * dw[k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < MIX_MAXN; ++k) {
+        if (k < n) {
+          const float dlk = wt[t][k] * (dw[k] - dot);
+          if (lane == 0) a.dl[((int64_t)t * a.B + b) * n + k] = dlk;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < d) { const float4 w = ld4(a.wg[t] + k * d + c); dq[i].x += dlk * w.x; dq[i].y += dlk * w.y; dq[i].z += dlk * w.z; dq[i].w += dlk * w.w; }
+          }
+        }
+      }
+    }
+    // d E_k = w_good[k] dfused_good + w_best[k] dfused_best + dq / n
+    float* dev = a.d_ev + b * (int64_t)n * d;
+#pragma unroll
+    for (int k = 0; k < MIX_MAXN; ++k) {
+      if (k < n) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = (i * 32 + lane) * 4;
+          if (c < d) {
+            float4 v;
+            v.x = wt[0][k] * df[0][i].x + wt[1][k] * df[1][i].x + inv_n * dq[i].x;
+            v.y = wt[0][k] * df[0][i].y + wt[1][k] * df[1][i].y + inv_n * dq[i].y;
+            v.z = wt[0][k] * df[0][i].z + wt[1][k] * df[1][i].z + inv_n * dq[i].z;
+            v.w = wt[0][k] * df[0][i].w + wt[1][k] * df[1][i].w + inv_n * dq[i].w;
+            st4(dev + k * d + c, v);
+          }
+        }
+      }
+    }
+  }
+  // tower LayerNorm weight / bias gradients: block reduction, one atomic per column per block
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < d) *reinterpret_cast<float4*>(&red[wib][c]) = pass == 0 ? acc_g[t][i] : acc_b[t][i];
+      }
+      __syncthreads();
+      float* dst = pass == 0 ? a.dgamma[t] : a.dbeta[t];
+      for (int c = threadIdx.x; c < d; c += 128) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) s += red[w][c];
+        atomicAdd(dst + c, s);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+struct HeadSaved { void* query; float *w, *st; void *xn, *z1, *a1, *z2, *a2; };
 static HeadSaved head_layout(Arena& A, const mmoe_head_cfg& cfg, int B, int dtype) {
   HeadSaved s{};
   const size_t es = dtype_size(dtype), Bz = (size_t)B; const int d = cfg.d, h1 = cfg.hidden, h2 = cfg.hidden / 2;
-  s.fused = (float*)A.take(2 * Bz * d * 4); s.query = (float*)A.take(Bz * d * 4); s.w = (float*)A.take(2 * Bz * cfg.n_expert * 4);
+  s.query = A.take(Bz * d * es); s.w = (float*)A.take(2 * Bz * cfg.n_expert * 4);
   s.st = (float*)A.take(2 * Bz * 2 * 4); s.xn = A.take(2 * Bz * d * es);
   s.z1 = A.take(2 * Bz * h1 * es); s.a1 = A.take(2 * Bz * h1 * es); s.z2 = A.take(2 * Bz * h2 * es); s.a2 = A.take(2 * Bz * h2 * es);
   return s;
 }
-struct HeadScratch { void *dz2, *dz1, *dxn; float *dfused, *dl; };
+struct HeadScratch { void *dz2, *dz1, *dxn; float* dl; };
 static HeadScratch head_scratch_layout(Arena& A, const mmoe_head_cfg& cfg, int B, int dtype) {
   HeadScratch t{};
   const size_t es = dtype_size(dtype), Bz = (size_t)B; const int d = cfg.d, h1 = cfg.hidden, h2 = cfg.hidden / 2;
   t.dz2 = A.take(2 * Bz * h2 * es); t.dz1 = A.take(2 * Bz * h1 * es); t.dxn = A.take(2 * Bz * d * es);
-  t.dfused = (float*)A.take(2 * Bz * d * 4); t.dl = (float*)A.take(2 * Bz * cfg.n_expert * 4);
+  t.dl = (float*)A.take(2 * Bz * cfg.n_expert * 4);
   return t;
 }
 static int check_head(const mmoe_head_cfg* cfg) {
@@ -90,6 +336,20 @@ static int check_head(const mmoe_head_cfg* cfg) {
   MMOE_CHECK(cfg->n_expert >= 1 && cfg->n_expert <= MIX_MAXN, "head: n_expert must be in [1,%d]", MIX_MAXN);
   MMOE_CHECK(cfg->hidden % 16 == 0 && cfg->hidden <= 1024, "head: unsupported tower_hidden %d", cfg->hidden);
   return 0;
+}
+
+template <typename T>
+static HeadFusedDev head_dev(const mmoe_call* c, const mmoe_head_cfg* cfg, const float* ev, const HeadSaved& s, const HeadIdx& ix) {
+  HeadFusedDev a{};
+  const void* const* P = c->params;
+  a.ev = ev;
+  for (int t = 0; t < 2; ++t) {
+    a.wg[t] = (const float*)P[ix.gw[t]]; a.bg[t] = (const float*)P[ix.gb[t]];
+    a.ln_w[t] = (const float*)P[ix.ln_w[t]]; a.ln_b[t] = (const float*)P[ix.ln_b[t]];
+  }
+  a.query_t = s.query; a.w = s.w; a.stats = s.st; a.xn = s.xn;
+  a.B = c->B; a.d = cfg->d; a.n = cfg->n_expert;
+  return a;
 }
 
 template <typename T>
@@ -104,19 +364,12 @@ static int head_fwd_t(const mmoe_call* c, const mmoe_head_cfg* cfg, const float*
   const float drop_p = c->training ? cfg->tower_drop_p : 0.f;
   uint32_t k0, k1;
   {
-    MixDev a{};
-    a.experts = ev; a.expert_stride = d; a.row_stride = (int64_t)n * d;
-    for (int t = 0; t < 2; ++t) for (int k = 0; k < n; ++k) a.sel[t][k] = k;
-    a.wg[0] = (const float*)P[ix.gw[0]]; a.wg[1] = (const float*)P[ix.gw[1]];
-    a.bg[0] = (const float*)P[ix.gb[0]]; a.bg[1] = (const float*)P[ix.gb[1]];
-    a.fused = s.fused; a.query_out = s.query; a.w = s.w; a.B = B; a.d = d; a.n = n;
-    mix_fwd_kernel<<<rows_grid(B, 8), 256, 0, st>>>(a);
-    MMOE_LAUNCH_OK("mix_fwd_kernel");
+    HeadFusedDev a = head_dev<T>(c, cfg, ev, s, ix);
+    if (d <= 768) head_mix_ln_fwd_kernel<T, 6><<<rows_grid(B, 8), 256, 0, st>>>(a);
+    else head_mix_ln_fwd_kernel<T, 8><<<rows_grid(B, 8), 256, 0, st>>>(a);
+    MMOE_LAUNCH_OK("head_mix_ln_fwd_kernel");
     if (gate_w != nullptr) MMOE_CUDA(cudaMemcpyAsync(gate_w, s.w, (size_t)2 * B * n * 4, cudaMemcpyDeviceToDevice, st));
   }
-  for (int t = 0; t < 2; ++t)
-    MMOE_TRY(layernorm_fwd(s.fused + (size_t)t * B * d, MMOE_F32, (const float*)P[ix.ln_w[t]], (const float*)P[ix.ln_b[t]],
-                           (char*)s.xn + (size_t)t * B * d * es, nullptr, s.st + (size_t)t * B * 2, B, d, dtype, st));
   {
     mmoe_gemm_problem p[2];
     for (int t = 0; t < 2; ++t) {
@@ -198,25 +451,19 @@ static int head_bwd_t(const mmoe_call* c, const mmoe_head_cfg* cfg, const float*
     }
     MMOE_TRY(gemm_grouped(p, 4, dtype, 0, st));
   }
-  for (int k = 0; k < 2; ++k) {
-    LnBwdArgs a{};
-    a.dy = (char*)t.dxn + (size_t)k * B * d * es; a.dy_dtype = dtype; a.x = s.fused + (size_t)k * B * d; a.x_dtype = MMOE_F32;
-    a.stats = s.st + (size_t)k * B * 2; a.gamma = (const float*)P[ix.ln_w[k]]; a.dx = t.dfused + (size_t)k * B * d;
-    a.dgamma = (float*)G[ix.ln_w[k]]; a.dbeta = (float*)G[ix.ln_b[k]]; a.rows = B; a.d = d; a.dtype = dtype;
-    MMOE_TRY(layernorm_bwd(a, st));
-  }
   {
-    MixDev a{};
-    a.experts = ev; a.expert_stride = d; a.row_stride = (int64_t)n * d;
-    for (int k2 = 0; k2 < 2; ++k2) for (int k = 0; k < n; ++k) a.sel[k2][k] = k;
-    a.wg[0] = (const float*)P[ix.gw[0]]; a.wg[1] = (const float*)P[ix.gw[1]];
-    a.w = s.w; a.dfused = t.dfused; a.dl = t.dl; a.dexperts = d_ev; a.accumulate_dexperts = 0; a.dquery = nullptr;
-    a.B = B; a.d = d; a.n = n;
-    mix_bwd_kernel<<<rows_grid(B, 8), 256, 0, st>>>(a, n);
-    MMOE_LAUNCH_OK("mix_bwd_kernel");
+    HeadFusedDev a = head_dev<T>(c, cfg, ev, s, ix);
+    a.dxn = t.dxn; a.dl = t.dl; a.d_ev = d_ev;
+    for (int k = 0; k < 2; ++k) { a.dgamma[k] = (float*)G[ix.ln_w[k]]; a.dbeta[k] = (float*)G[ix.ln_b[k]]; }
+    int64_t blocks = ((int64_t)B + 3) / 4;
+    const int64_t cap = (int64_t)sm_count() * 4;
+    if (blocks > cap) blocks = cap;
+    if (d <= 768) head_ln_mix_bwd_kernel<T, 6><<<(int)blocks, 128, 0, st>>>(a);
+    else head_ln_mix_bwd_kernel<T, 8><<<(int)blocks, 128, 0, st>>>(a);
+    MMOE_LAUNCH_OK("head_ln_mix_bwd_kernel");
   }
   for (int k = 0; k < 2; ++k)
-    MMOE_TRY(small_wgrad(t.dl + (size_t)k * B * n, s.query, (float*)G[ix.gw[k]], (float*)G[ix.gb[k]], B, d, n, st));
+    MMOE_TRY(small_wgrad(t.dl + (size_t)k * B * n, s.query, dtype, (float*)G[ix.gw[k]], (float*)G[ix.gb[k]], B, d, n, st));
   return 0;
 }
 
@@ -266,5 +513,5 @@ extern "C" int mmoe_dense_gate_bwd(const float* x, const float* wg, const float*
   if (B == 0) return 0;
   dense_gate_bwd_kernel<<<rows_grid(B, 8), 256, 0, (cudaStream_t)stream>>>(w, dw, wg, dl, dx, B, d, n);
   MMOE_LAUNCH_OK("dense_gate_bwd_kernel");
-  return small_wgrad(dl, x, dwg, dbg, B, d, n, (cudaStream_t)stream);
+  return small_wgrad(dl, x, MMOE_F32, dwg, dbg, B, d, n, (cudaStream_t)stream);
 }

@@ -197,7 +197,7 @@ static __global__ void __launch_bounds__(256) mix_bwd_kernel(const MixDev a, int
 
 // ---------------------------------------------------------------- dW[k][c] += sum_b coef[b][k] * X[b][c]; db[k] += sum_b coef[b][k]
 // (gate weight gradients: k <= 8 outputs).  grid = (ceil(d/64), row chunks), 256 threads.
-static __global__ void __launch_bounds__(256) small_wgrad_kernel(const float* __restrict__ coef, const float* __restrict__ X,
+static __global__ void __launch_bounds__(256) small_wgrad_kernel(const float* __restrict__ coef, const void* __restrict__ X, int x_dtype,
                                                           float* __restrict__ dW, float* __restrict__ db, int64_t B, int d, int n,
                                                           int64_t rows_per_block) {
   __shared__ float red[4][MIX_MAXN][64];
@@ -208,7 +208,7 @@ static __global__ void __launch_bounds__(256) small_wgrad_kernel(const float* __
 #pragma unroll
   for (int k = 0; k < MIX_MAXN; ++k) acc[k] = accb[k] = 0.f;
   for (int64_t b = b0 + sub; b < b1; b += 4) {
-    const float x = c < d ? X[b * d + c] : 0.f;
+    const float x = c < d ? load_as_f(X, b * d + c, x_dtype) : 0.f;
 #pragma unroll
     for (int k = 0; k < MIX_MAXN; ++k)
       if (k < n) { const float cf = coef[b * n + k]; acc[k] = fmaf(cf, x, acc[k]); accb[k] += cf; }
@@ -228,13 +228,13 @@ static __global__ void __launch_bounds__(256) small_wgrad_kernel(const float* __
   }
 }
 
-inline int small_wgrad(const float* coef, const float* X, float* dW, float* db, int64_t B, int d, int n, cudaStream_t s) {
+inline int small_wgrad(const float* coef, const void* X, int x_dtype, float* dW, float* db, int64_t B, int d, int n, cudaStream_t s) {
   int64_t chunks = (B + 255) / 256;
   if (chunks > 64) chunks = 64;
   if (chunks < 1) chunks = 1;
   const int64_t rpb = (B + chunks - 1) / chunks;
   dim3 grid((d + 63) / 64, (unsigned)chunks);
-  small_wgrad_kernel<<<grid, 256, 0, s>>>(coef, X, dW, db, B, d, n, rpb);
+  small_wgrad_kernel<<<grid, 256, 0, s>>>(coef, X, x_dtype, dW, db, B, d, n, rpb);
   MMOE_LAUNCH_OK("small_wgrad_kernel");
   return 0;
 }

@@ -394,7 +394,7 @@ static int home_bwd_t(const mmoe_call* c, const mmoe_home_cfg* cfg, const float*
     MMOE_LAUNCH_OK("mix_bwd_kernel");
   }
   for (int k = 0; k < 2; ++k)
-    MMOE_TRY(small_wgrad(t.dl + (size_t)k * B * n, s.shared_f, (float*)G[ix.gate_w(k)], (float*)G[ix.gate_b(k)], B, d, n, st));
+    MMOE_TRY(small_wgrad(t.dl + (size_t)k * B * n, s.shared_f, MMOE_F32, (float*)G[ix.gate_w(k)], (float*)G[ix.gate_b(k)], B, d, n, st));
   // SelfGate backward
   {
     float* host_tbl[16];

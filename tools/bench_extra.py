@@ -42,8 +42,10 @@ def timeit(fn, warm=3, reps=10):
 
 def bench_head():
     head = M.TwoTaskMMoE().to(dev).train()
-    for mode in ("fp32", "bf16"):
-        for B in (256, 4096, 16384, 65536):
+    modes = os.environ.get("HEAD_MODES", "fp32,bf16").split(",")
+    sizes = [int(x) for x in os.environ.get("HEAD_BS", "256,4096,16384,65536").split(",")]
+    for mode in modes:
+        for B in sizes:
             ev = torch.randn(B, 6, 768, device=dev, requires_grad=True)
 
             def step():
