@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import argparse
 import ctypes as C
+import gc
 import json
 import os
 import subprocess
@@ -312,23 +313,42 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step(resident)
     barrier()
-    L.mmoe_launch_count(1)
-    L.mmoe_gemm_timing(1)
+    L.mmoe_gemm_timing(0 if os.environ.get("BENCH_NO_GEMM_TIMING") else 128 * args.steps)   # event pairs created up front
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER"):
+        sampler.start()                            # first NVML calls happen during the extra warm-up step below
+    step(resident)
     barrier()
+    L.mmoe_gemm_timing_read(C.byref(C.c_double()), C.byref(C.c_double()), C.byref(C.c_int64()), 1)
+    sampler.samples.clear()
+    L.mmoe_launch_count(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gc.collect()
+    gc.disable()          # a generation-2 collection inside the timed loop stalls the enqueueing thread for tens of ms
+    barrier()
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    for e in step_ev:
+        e.record()                # torch creates the CUDA event lazily at the first record: do that outside the timed loop
+    torch.cuda.synchronize()
     ev0.record()
     t_host = time.perf_counter()
-    for _ in range(args.steps):
+    step_ev[0].record()
+    host_t = [time.perf_counter()]
+    for i in range(args.steps):
+        if i >= 2 and not os.environ.get("BENCH_NO_THROTTLE"):
+            step_ev[i - 1].synchronize()       # stay at most two steps ahead of the device (bounded launch-queue depth)
         loss = step(resident)
+        step_ev[i + 1].record()
+        host_t.append(time.perf_counter())
     host_ms_step = (time.perf_counter() - t_host) * 1e3 / args.steps     # time the host needs to ENQUEUE a step
     ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     L.mmoe_gemm_timing(0)
     ms_total = ev0.elapsed_time(ev1)
+    per_step = [step_ev[i].elapsed_time(step_ev[i + 1]) for i in range(args.steps)]
+    slowest_step = max(range(args.steps), key=lambda i: per_step[i])
+    per_step.sort()
     launches = int(L.mmoe_launch_count(1))
     g_ms, g_fl, g_n = C.c_double(), C.c_double(), C.c_int64()
     L.mmoe_gemm_timing_read(C.byref(g_ms), C.byref(g_fl), C.byref(g_n), 1)
@@ -400,6 +420,8 @@ def main():
                     "note": "pinned host batch copied on a side stream (double buffered) every step; loss.item() read back every step"},
             "gpu_launches": launches,
             "host_enqueue_ms_per_step": host_ms_step,
+            "ms_per_step_min_median_max": [per_step[0], per_step[len(per_step) // 2], per_step[-1]], "slowest_step": slowest_step,
+            "host_ms_max_step": max((host_t[i + 1] - host_t[i]) * 1e3 for i in range(args.steps)),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 grouped GEMM, all launches of the timed region)",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,

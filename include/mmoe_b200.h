@@ -103,7 +103,8 @@ int mmoe_gemm_grouped(const mmoe_gemm_problem* problems /*host*/, int n_problems
 
 /* Live timing of the GEMM launches (bench.py's roofline): while enabled, CUDA events are recorded on the launching
  * stream around every mmoe_gemm_grouped launch (also those issued by the module entry points).  _read sums the
- * durations / algorithmic FLOPs (2*M*N*K) recorded since the last read — call it after a device synchronize. */
+ * durations / algorithmic FLOPs (2*M*N*K) recorded since the last read — call it after a device synchronize.
+ * enable > 1 also pre-creates event pairs for that many launches, so no event is created inside a timed region. */
 int mmoe_gemm_timing(int enable);
 int mmoe_gemm_timing_read(double* total_ms, double* total_flops, int64_t* launches, int tc_only);
 

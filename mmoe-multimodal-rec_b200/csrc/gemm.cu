@@ -207,15 +207,25 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const __grid_constant__ 
 // ------------------------------------------------------------------------------------------
 // tcgen05 kernel
 // ------------------------------------------------------------------------------------------
-constexpr int TBM = 128, TBN = 256, TBK = 64, TSTAGES = 4;
+constexpr int TBM = 128, TBN = 256, TBK = 64;
 constexpr int TA_BYTES = TBM * TBK * 2;   // 16 KB
-constexpr int TB_BYTES = TBN * TBK * 2;   // 32 KB
-constexpr int TSTAGE_BYTES = TA_BYTES + TB_BYTES;
+// One CTA per tile: 4 stages of {A 128x64, B 256x64} = 4 x 48 KB.  CTA pair (cta_group::2) on a 256 x 256 tile: each CTA
+// stages its own 128 rows of A and HALF of B (128 x 64), 6 stages of 32 KB — the same 192 KB, but a third less
+// L2 -> shared-memory traffic per FLOP, which is what bounds the one-CTA kernel on the large GEMMs.
+template <int CTAS> struct TcCfg {
+  static constexpr int STAGES = CTAS == 2 ? 6 : 4;
+  static constexpr int B_BYTES = (TBN / CTAS) * TBK * 2;
+  static constexpr int STAGE_BYTES = TA_BYTES + B_BYTES;
+};
+constexpr int TC_PIPE_BYTES = 4 * (TA_BYTES + TBN * TBK * 2);
+static_assert(TcCfg<1>::STAGES * TcCfg<1>::STAGE_BYTES == TC_PIPE_BYTES && TcCfg<2>::STAGES * TcCfg<2>::STAGE_BYTES == TC_PIPE_BYTES, "pipeline bytes");
+constexpr int TMAX_STAGES = 6;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TEPI_WARP_BYTES = 4096;     // per-warp staging slab: 32 rows x 128 B
 constexpr int TEPI_BYTES = TC_EPI_WARPS * TEPI_WARP_BYTES;
 constexpr int TEPI_BIAS_BYTES = 2 * TBN * 4;   // per accumulator stage: the tile's 256 bias values (fast epilogue)
-constexpr int TC_SMEM_BYTES = TSTAGES * TSTAGE_BYTES + TEPI_BYTES + 128 /*barriers + TMEM slot*/ + TEPI_BIAS_BYTES;   // 231,552 B of the 232,448 B limit
+constexpr int TBAR_BYTES = 256;              // 16 mbarriers + the TMEM base slot
+constexpr int TC_SMEM_BYTES = TC_PIPE_BYTES + TEPI_BYTES + TBAR_BYTES + TEPI_BIAS_BYTES;   // 231,680 B of the 232,448 B limit
 constexpr int TC_THREADS = 128 + 32 * TC_EPI_WARPS;
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -292,6 +302,45 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants.  Barriers that both CTAs' hardware units signal live in the LEADER (cluster rank 0):
+// `mapa` turns a local shared-memory address into the leader's address of the same offset.
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// TMA load issued by either CTA of the pair into ITS OWN shared memory, completing bytes on the leader's barrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// commit of the pair's MMAs: one arrival on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// one lane of a converged warp (the compiler keeps warp-uniform operands in uniform registers under this predicate,
+// which it does not do under `lane == 0`)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0u;
+}
 // UMMA shared-memory matrix descriptor (SM100): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 |
 // layout SWIZZLE_128B (2) <<61.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -336,8 +385,16 @@ __device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int tile) {
 // BN: tile width (compile-time so the TMA issue loop and the instruction descriptor are constants — the pipeline is
 // latency-critical and a runtime width cost 5-14%).  RICH: the fast epilogue also handles GELU / sigmoid and a
 // pre-activation copy (kept out of the lean instantiation: the extra code slowed the ReLU/bias tiles by 15%).
-template <int BN, bool RICH>
+// CTAS = 2: the two CTAs of a cluster work on one 256 x BN tile with tcgen05.mma.cta_group::2 (M = 256).  Both run the
+// TMA producer (own 128 rows of A, own half of B) and the epilogue (own 128 accumulator rows, in their own TMEM);
+// only the leader issues MMAs.
+template <int BN, bool RICH, int CTAS>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+  constexpr int TSTAGES = TcCfg<CTAS>::STAGES, TB_BYTES = TcCfg<CTAS>::B_BYTES, TSTAGE_BYTES = TcCfg<CTAS>::STAGE_BYTES;
+  constexpr int BN_CTA = BN / CTAS;                      // B rows this CTA stages
+  const uint32_t crank = CTAS == 2 ? cluster_rank() : 0u;
+  const int first_tile = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CTAS == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   // SWIZZLE_128B tiles need 1024-byte alignment; the kernel has no static shared memory, so the dynamic window starts
   // at the (aligned) base of the CTA's shared memory.  Checked, not assumed.
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -348,94 +405,124 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   const uint32_t smem_b0 = smem_base + TSTAGES * TA_BYTES;
   float* epi_stage = reinterpret_cast<float*>(smem_gen + TSTAGES * TSTAGE_BYTES);
   const uint32_t bar_base = smem_base + TSTAGES * TSTAGE_BYTES + TEPI_BYTES;
-  // barrier layout: full[4], empty[4], tmem_full[2], tmem_empty[2], then the TMEM base slot
+  // barrier layout: full[6], empty[6], tmem_full[2], tmem_empty[2] (16 x 8 B), then the TMEM base slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (TSTAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * TSTAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * TSTAGES + 2 + s); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + TSTAGES * TSTAGE_BYTES + TEPI_BYTES + 8 * (2 * TSTAGES + 4));
+  auto empty_bar = [&](int s) { return bar_base + 8u * (TMAX_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * TMAX_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * TMAX_STAGES + 2 + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + TSTAGES * TSTAGE_BYTES + TEPI_BYTES + 8 * (2 * TMAX_STAGES + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), TC_EPI_WARPS); }
+    // the leader's tmem_empty collects the epilogue warps of BOTH CTAs
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), TC_EPI_WARPS * CTAS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (CTAS == 2) cluster_sync_all();        // both CTAs' barriers exist before any remote arrival; also required before a pair allocation
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // The whole warp walks the loop (warp-uniform control flow keeps addresses and descriptors in uniform registers:
+    // with the loop inside `if (lane == 0)` the compiler built them in vector registers and paid 7 R2UR per MMA);
+    // lane 0 issues.
+    {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      auto load = [&](uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+        if (CTAS == 2) tma_load_2d_pair(dst, map, bar, c0, c1); else tma_load_2d(dst, map, bar, c0, c1);
+      };
+      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
         const TileInfo t = decode_tile(p, tile);
         const TcGroup& g = p.g[t.gi];
-        const int m0 = t.m_blk * TBM, n0 = t.n_blk * BN;
-        constexpr uint32_t stage_tx = (uint32_t)(TA_BYTES + BN * TBK * 2);
+        const int m0 = (t.m_blk * CTAS + (int)crank) * TBM, n0 = t.n_blk * BN + (int)crank * BN_CTA;
+        constexpr uint32_t stage_tx = (uint32_t)(CTAS * (TA_BYTES + BN_CTA * TBK * 2));     // both CTAs' bytes land on the leader's barrier
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), stage_tx);
+          const uint32_t fb = CTAS == 2 ? map_to_cta(full_bar(stage), 0u) : full_bar(stage);
           const uint32_t sa = smem_a0 + stage * TA_BYTES, sb = smem_b0 + stage * TB_BYTES;
           const int k0 = kb * TBK;
-          if (g.a_major == 0) {
-            tma_load_2d(sa, &g.tma_a, full_bar(stage), k0, m0);                 // box {64 k, 128 m}
-          } else {
+          if (elect_one()) {
+            if (crank == 0) mbar_expect_tx(full_bar(stage), stage_tx);
+            if (g.a_major == 0) {
+              load(sa, &g.tma_a, fb, k0, m0);                                   // box {64 k, 128 m}
+            } else {
 #pragma unroll
-            for (int j = 0; j < TBM / 64; ++j)                                  // boxes {64 m, 64 k}
-              tma_load_2d(sa + j * (TBK * 128), &g.tma_a, full_bar(stage), m0 + j * 64, k0);
-          }
-          if (g.b_major == 0) {
-            tma_load_2d(sb, &g.tma_b, full_bar(stage), k0, n0);                 // box {64 k, bn n}
-          } else {
+              for (int j = 0; j < TBM / 64; ++j)                                // boxes {64 m, 64 k}
+                load(sa + j * (TBK * 128), &g.tma_a, fb, m0 + j * 64, k0);
+            }
+            if (g.b_major == 0) {
+              load(sb, &g.tma_b, fb, k0, n0);                                   // box {64 k, BN_CTA n}
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)                                   // boxes {64 n, 64 k}
-              tma_load_2d(sb + j * (TBK * 128), &g.tma_b, full_bar(stage), n0 + j * 64, k0);
+              for (int j = 0; j < BN_CTA / 64; ++j)                             // boxes {64 n, 64 k}
+                load(sb + j * (TBK * 128), &g.tma_b, fb, n0 + j * 64, k0);
+            }
           }
+          __syncwarp();
           if (++stage == TSTAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    if (crank == 0) {
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
         const TileInfo t = decode_tile(p, tile);
         const TcGroup& g = p.g[t.gi];
-        // instruction descriptor: D fp32, A/B f16|bf16, majors, N>>3, M>>4
+        // instruction descriptor: D fp32, A/B f16|bf16, majors, N>>3, M>>4  (M = 256 across the pair)
         const uint32_t idesc = (1u << 4) | ((uint32_t)p.fmt << 7) | ((uint32_t)p.fmt << 10) |
                                ((uint32_t)g.a_major << 15) | ((uint32_t)g.b_major << 16) |
-                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TBM * CTAS) >> 4) << 24);
+        // K-major: 8-row groups 1024 B apart (SBO), 32 B per UMMA_K step inside the 128 B swizzle row.
+        // MN-major: 64-element column blocks TBK*128 B apart (LBO), 8-k groups 1024 B apart (SBO),
+        //           16 k-rows (2048 B) per UMMA_K step.
+        // The start-address field (bits 0-13, address >> 4) is the only part that moves: template + offset.
+        const uint64_t adesc_t = g.a_major == 0 ? umma_desc(0, 16, 1024) : umma_desc(0, TBK * 128, 1024);
+        const uint64_t bdesc_t = g.b_major == 0 ? umma_desc(0, 16, 1024) : umma_desc(0, TBK * 128, 1024);
+        const uint32_t a_step = g.a_major == 0 ? (32u >> 4) : (2048u >> 4), b_step = g.b_major == 0 ? (32u >> 4) : (2048u >> 4);
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * TBN);
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_a0 + stage * TA_BYTES, sb = smem_b0 + stage * TB_BYTES;
+          const uint64_t adesc0 = adesc_t | (uint64_t)((smem_a0 + stage * TA_BYTES) >> 4);
+          const uint64_t bdesc0 = bdesc_t | (uint64_t)((smem_b0 + stage * TB_BYTES) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < TBK / 16; ++k) {
-            // K-major: 8-row groups 1024 B apart (SBO), 32 B per UMMA_K step inside the 128 B swizzle row.
-            // MN-major: 64-element column blocks TBK*128 B apart (LBO), 8-k groups 1024 B apart (SBO),
-            //           16 k-rows (2048 B) per UMMA_K step.
-            const uint64_t adesc = g.a_major == 0 ? umma_desc(sa + k * 32, 16, 1024) : umma_desc(sa + k * 2048, TBK * 128, 1024);
-            const uint64_t bdesc = g.b_major == 0 ? umma_desc(sb + k * 32, 16, 1024) : umma_desc(sb + k * 2048, TBK * 128, 1024);
-            tc_mma_f16(tmem_d, adesc, bdesc, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < TBK / 16; ++k) {
+              const uint64_t adesc = adesc0 + (uint64_t)(k * a_step), bdesc = bdesc0 + (uint64_t)(k * b_step);
+              if (CTAS == 2) tc_mma_f16_pair(tmem_d, adesc, bdesc, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+              else tc_mma_f16(tmem_d, adesc, bdesc, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+            }
+            // frees the smem slot (in both CTAs) once these MMAs have read it
+            if (CTAS == 2) tc_commit_pair(empty_bar(stage)); else tc_commit(empty_bar(stage));
           }
-          tc_commit(empty_bar(stage));      // frees the smem slot once these MMAs have read it
+          __syncwarp();
           if (++stage == TSTAGES) { stage = 0; phase ^= 1u; }
         }
-        tc_commit(tfull_bar(as));           // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (elect_one()) {
+          if (CTAS == 2) tc_commit_pair(tfull_bar(as)); else tc_commit(tfull_bar(as));
+        }
+        __syncwarp();
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
@@ -448,17 +535,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     const int quad = warp & 3;
     const int half = ew >> 2;
     float* st = epi_stage + ew * (TEPI_WARP_BYTES / 4);      // 32 x 32 fp32 slab (general path) / 32 x 128 B rows (fast path)
-    float* bias_tab = reinterpret_cast<float*>(smem_gen + TSTAGES * TSTAGE_BYTES + TEPI_BYTES + 128);
+    float* bias_tab = reinterpret_cast<float*>(smem_gen + TSTAGES * TSTAGE_BYTES + TEPI_BYTES + TBAR_BYTES);
     const uint32_t st_addr = smem_u32(st);
     bool store_pending = false;
     const int sub = lane >> 4;               // row of the pair this half-warp handles
     const int cl = (lane & 15) * 2;          // first of the lane's two columns inside a 32-column chunk
     int as = 0; uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
       const TileInfo t = decode_tile(p, tile);
       const TcGroup& g = p.g[t.gi];
       const EpiDev& E = g.epi;
-      const int m0 = t.m_blk * TBM + quad * 32, n0 = t.n_blk * BN;
+      const int m0 = (t.m_blk * CTAS + (int)crank) * TBM + quad * 32, n0 = t.n_blk * BN;
       const bool first = (t.split == 0);
       const int N = g.N;
       const int rows = min(32, g.M - m0);    // may be <= 0 for a ragged last tile
@@ -543,7 +630,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
             float v0 = __uint_as_float(v[j]) + bb.x;
             float v1 = __uint_as_float(v[j + 1]) + bb.y;
             if (act == 1) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-            else if (RICH && act == 2) { v0 = gelu_f(v0); v1 = gelu_f(v1); }
+            else if (RICH && act == 2) { v0 = gelu_fast_f(v0); v1 = gelu_fast_f(v1); }
             else if (RICH && act == 3) { v0 = sigmoid_f(v0); v1 = sigmoid_f(v1); }
             if (thresh != 0u) {
               const uint32_t h = drop_hash(dk0, dk1, (idx0 + j) >> 1);
@@ -572,7 +659,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (lane == 0) {
+          if (CTAS == 2) mbar_arrive_cluster(map_to_cta(tempty_bar(as), 0u)); else mbar_arrive(tempty_bar(as));
+        }
         if (++as == 2) { as = 0; aphase ^= 1u; }
         continue;
       }
@@ -628,14 +717,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
               *reinterpret_cast<uint32_t*>(preact + (m * ldo + n) * 2) = pk;
             }
             if (act == 1) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-            else if (act == 2) { v0 = gelu_f(v0); v1 = gelu_f(v1); }
+            else if (act == 2) { v0 = gelu_fast_f(v0); v1 = gelu_fast_f(v1); }
             else if (act == 3) { v0 = sigmoid_f(v0); v1 = sigmoid_f(v1); }
             if (bwd_mode != 0) {
               float a0, a1;
               if (is_bf16) { a0 = __uint_as_float(ax[u] << 16); a1 = __uint_as_float(ax[u] & 0xFFFF0000u); }
               else { const __half2 hh = *reinterpret_cast<const __half2*>(&ax[u]); a0 = __low2float(hh); a1 = __high2float(hh); }
               if (bwd_mode == 1) { v0 = (a0 != 0.f) ? v0 * dscale : 0.f; v1 = (a1 != 0.f) ? v1 * dscale : 0.f; }
-              else if (bwd_mode == 2) { v0 *= gelu_grad_f(a0); v1 *= gelu_grad_f(a1); }
+              else if (bwd_mode == 2) { v0 *= gelu_grad_fast_f(a0); v1 *= gelu_grad_fast_f(a1); }
               else { const float s0 = sigmoid_f(a0), s1 = sigmoid_f(a1); v0 *= s0 * (1.f - s0); v1 *= s1 * (1.f - s1); }
             }
             if (thresh != 0u) {
@@ -666,16 +755,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (lane == 0) {
+          if (CTAS == 2) mbar_arrive_cluster(map_to_cta(tempty_bar(as), 0u)); else mbar_arrive(tempty_bar(as));
+        }
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
     if (store_pending && lane == 0) tma_store_wait_all();     // bulk stores must complete before the CTA's smem goes away
   }
   tc_fence_before();
-  __syncthreads();
+  // pair: neither CTA may free TMEM or exit while the other can still signal its barriers or read its shared memory
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (CTAS == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -741,25 +834,31 @@ static int launch_tc(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream_t
   P.fmt = dtype == MMOE_BF16 ? 1 : 0;
   // tile width: small-batch problems (fuse experts, heads) are latency-bound single-wave launches; narrower tiles put
   // more SMs on them and shorten the per-tile MMA chain (N = 64 costs a quarter of the cycles of N = 256 per K step)
-  int bn = TBN;
+  int bn = TBN, ctas = 1;
   {
-    auto count_tiles = [&](int w) {
+    auto count_tiles = [&](int w, int h) {
       long t = 0;
       for (int i = 0; i < n; ++i) {
         const int kb = (pr[i].K + TBK - 1) / TBK;
         int ks = pr[i].k_splits < 1 ? 1 : pr[i].k_splits;
         if (ks > kb) ks = kb;
-        t += (long)((pr[i].M + TBM - 1) / TBM) * ((pr[i].N + w - 1) / w) * ks;
+        t += (long)((pr[i].M + h - 1) / h) * ((pr[i].N + w - 1) / w) * ks;
       }
       return t;
     };
     static const int forced = getenv("MMOE_DEBUG_BN") ? atoi(getenv("MMOE_DEBUG_BN")) : 0;
+    static const int forced_ctas = getenv("MMOE_DEBUG_CTAS") ? atoi(getenv("MMOE_DEBUG_CTAS")) : 0;
     if (forced == 64 || forced == 128 || forced == 256) bn = forced;
     else {
-      while (bn > 64 && count_tiles(bn) < sm_count()) bn >>= 1;
+      while (bn > 64 && count_tiles(bn, TBM) < sm_count()) bn >>= 1;
     }
+    // CTA pairs on 256 x 256 tiles once there is at least a wave of them (74 pairs on 148 SMs)
+    if (forced_ctas == 1 || forced_ctas == 2) ctas = forced_ctas;
+    else if (bn == TBN && count_tiles(TBN, 2 * TBM) >= sm_count() / 2) ctas = 2;
+    if (ctas == 2 && forced == 0) bn = TBN;
   }
   P.bn = bn;
+  const int tile_m = TBM * ctas;
   int tiles = 0;
   bool rich = false;
   for (int i = 0; i < n; ++i) {
@@ -769,7 +868,7 @@ static int launch_tc(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream_t
     g.a_major = q.a_major; g.b_major = q.b_major;
     if (q.a_major == 0) MMOE_TRY(make_tmap(&g.tma_a, q.a, dtype, q.M, q.K, q.lda, TBM));
     else                MMOE_TRY(make_tmap(&g.tma_a, q.a, dtype, q.K, q.M, q.lda, TBK));
-    if (q.b_major == 0) MMOE_TRY(make_tmap(&g.tma_b, q.b, dtype, q.N, q.K, q.ldb, bn));
+    if (q.b_major == 0) MMOE_TRY(make_tmap(&g.tma_b, q.b, dtype, q.N, q.K, q.ldb, bn / ctas));
     else                MMOE_TRY(make_tmap(&g.tma_b, q.b, dtype, q.K, q.N, q.ldb, TBK));
     MMOE_TRY(fill_epi(&g.epi, q, dtype));
     {
@@ -784,7 +883,7 @@ static int launch_tc(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream_t
       if (fast && e.preact != nullptr) MMOE_TRY(make_tmap(&g.tma_pre, e.preact, dtype, q.M, q.N, e.ldo, 32));
       if (fast && (e.preact != nullptr || e.act >= 2)) rich = true;
     }
-    g.tiles_m = (q.M + TBM - 1) / TBM;
+    g.tiles_m = (q.M + tile_m - 1) / tile_m;
     g.tiles_n = (q.N + bn - 1) / bn;
     g.kb_total = (q.K + TBK - 1) / TBK;
     int ks = q.k_splits < 1 ? 1 : q.k_splits;
@@ -797,12 +896,13 @@ static int launch_tc(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream_t
   P.total_tiles = tiles;
   if (tiles == 0) return 0;
   using TcKernel = void (*)(const TcParams);
-  static const TcKernel kernels[3][2] = {{gemm_tc_kernel<64, false>, gemm_tc_kernel<64, true>},
-                                         {gemm_tc_kernel<128, false>, gemm_tc_kernel<128, true>},
-                                         {gemm_tc_kernel<256, false>, gemm_tc_kernel<256, true>}};
+  static const TcKernel kernels[4][2] = {{gemm_tc_kernel<64, false, 1>, gemm_tc_kernel<64, true, 1>},
+                                         {gemm_tc_kernel<128, false, 1>, gemm_tc_kernel<128, true, 1>},
+                                         {gemm_tc_kernel<256, false, 1>, gemm_tc_kernel<256, true, 1>},
+                                         {gemm_tc_kernel<256, false, 2>, gemm_tc_kernel<256, true, 2>}};
   static bool attr_set = false;
   if (!attr_set) {
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 4; ++i)
       for (int j = 0; j < 2; ++j)
         MMOE_CUDA(cudaFuncSetAttribute(kernels[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attr_set = true;
@@ -812,8 +912,25 @@ static int launch_tc(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream_t
   // behind it.
   int avail = sm_count() - g_sm_reserve.load(std::memory_order_relaxed);
   if (avail < 1) avail = 1;
-  const int grid = tiles < avail ? tiles : avail;
-  kernels[bn == 64 ? 0 : (bn == 128 ? 1 : 2)][rich ? 1 : 0]<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(P);
+  if (ctas == 2) {
+    MMOE_CHECK(bn == TBN, "the CTA-pair kernel is built for 256-wide tiles only");
+    int pairs = avail / 2;
+    if (pairs < 1) pairs = 1;
+    if (tiles < pairs) pairs = tiles;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    MMOE_CUDA(cudaLaunchKernelEx(&cfg, kernels[3][rich ? 1 : 0], P));
+  } else {
+    const int grid = tiles < avail ? tiles : avail;
+    kernels[bn == 64 ? 0 : (bn == 128 ? 1 : 2)][rich ? 1 : 0]<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(P);
+  }
   MMOE_LAUNCH_OK("gemm_tc_kernel");
   return 0;
 }
@@ -922,6 +1039,16 @@ extern "C" int mmoe_gemm_grouped(const mmoe_gemm_problem* problems, int n_proble
 }
 
 extern "C" int mmoe_gemm_timing(int enable) {
+  if (enable > 1) {
+    // pre-create event pairs for `enable` launches: cudaEventCreate inside a timed region stalls the enqueueing thread
+    // (a 40-300 ms hiccup in the second timed step of bench.py before this existed)
+    std::lock_guard<std::mutex> lk(mmoe::g_time_mu);
+    while ((int)mmoe::g_event_pool.size() < 2 * enable) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) break;
+      mmoe::g_event_pool.push_back(e);
+    }
+  }
   mmoe::g_timing_on.store(enable ? 1 : 0);
   return 0;
 }

@@ -314,6 +314,266 @@ __global__ void __launch_bounds__(128, 2) head_ln_mix_bwd_kernel(const HeadFused
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Register-resident variants for the common geometry (n_expert = NE, expert_dim <= NV*128): a warp first issues ALL of
+// its sample's expert-vector loads (NE*NV independent 16-byte loads per lane = 18 KB in flight per warp), then does
+// every pass from registers.  The v1 kernels above re-read expert_vecs through L1 for each pass and were latency-bound
+// (forward 2.2 TB/s, backward 1.35 TB/s of algorithmic traffic at B = 65536).
+// ------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ void st4_as(T* p, float4 v);
+template <> __device__ __forceinline__ void st4_as<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+template <> __device__ __forceinline__ void st4_as<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u; u.x = *reinterpret_cast<const uint32_t*>(&lo); u.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+template <> __device__ __forceinline__ void st4_as<__half>(__half* p, float4 v) {
+  const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+  uint2 u; u.x = *reinterpret_cast<const uint32_t*>(&lo); u.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+template <typename T> __device__ __forceinline__ float4 ld4_as(const T* p);
+template <> __device__ __forceinline__ float4 ld4_as<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float4 ld4_as<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
+}
+template <> __device__ __forceinline__ float4 ld4_as<__half>(const __half* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ void fma4(float4& acc, float s, float4 v) { acc.x = fmaf(s, v.x, acc.x); acc.y = fmaf(s, v.y, acc.y); acc.z = fmaf(s, v.z, acc.z); acc.w = fmaf(s, v.w, acc.w); }
+
+template <typename T, int NE, int NV>
+__global__ void __launch_bounds__(128, 2) head_fwd_reg_kernel(const HeadFusedDev a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int d = a.d;
+  const float inv_d = 1.f / (float)d, inv_n = 1.f / (float)NE;
+  for (int64_t b = warp0; b < a.B; b += nw) {
+    const float* evb = a.ev + b * (int64_t)NE * d;
+    float4 E[NE][NV];
+#pragma unroll
+    for (int k = 0; k < NE; ++k)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        E[k][i] = c < d ? __ldcs(reinterpret_cast<const float4*>(evb + k * d + c)) : make_float4(0, 0, 0, 0);
+      }
+    float4 q[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      q[i] = E[0][i];
+#pragma unroll
+      for (int k = 1; k < NE; ++k) { q[i].x += E[k][i].x; q[i].y += E[k][i].y; q[i].z += E[k][i].z; q[i].w += E[k][i].w; }
+      q[i].x *= inv_n; q[i].y *= inv_n; q[i].z *= inv_n; q[i].w *= inv_n;
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) st4_as<T>((T*)a.query_t + b * d + c, q[i]);
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      float wk[NE];
+#pragma unroll
+      for (int k = 0; k < NE; ++k) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = (i * 32 + lane) * 4;
+          if (c < d) acc += dot4(q[i], __ldg(reinterpret_cast<const float4*>(a.wg[t] + k * d + c)));
+        }
+        wk[k] = acc;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int k = 0; k < NE; ++k) wk[k] += __shfl_xor_sync(0xffffffffu, wk[k], o);
+      float m = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < NE; ++k) { wk[k] += a.bg[t][k]; m = fmaxf(m, wk[k]); }
+      float ssum = 0.f;
+#pragma unroll
+      for (int k = 0; k < NE; ++k) { wk[k] = expf(wk[k] - m); ssum += wk[k]; }
+      const float inv = 1.f / ssum;
+#pragma unroll
+      for (int k = 0; k < NE; ++k) wk[k] *= inv;
+      if (lane < NE) {
+        float mine = wk[0];
+#pragma unroll
+        for (int k = 1; k < NE; ++k) mine = lane == k ? wk[k] : mine;
+        a.w[((int64_t)t * a.B + b) * NE + lane] = mine;
+      }
+      float4 f[NV];
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        f[i] = make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < NE; ++k) fma4(f[i], wk[k], E[k][i]);
+        sum += f[i].x + f[i].y + f[i].z + f[i].w;
+      }
+      const float mean = warp_sum(sum) * inv_d;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < d) { const float x0 = f[i].x - mean, x1 = f[i].y - mean, x2 = f[i].z - mean, x3 = f[i].w - mean; sq += x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3; }
+      }
+      const float rstd = rsqrtf(warp_sum(sq) * inv_d + 1e-5f);
+      if (lane == 0) { a.stats[((int64_t)t * a.B + b) * 2] = mean; a.stats[((int64_t)t * a.B + b) * 2 + 1] = rstd; }
+      T* xo = (T*)a.xn + ((int64_t)t * a.B + b) * d;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < d) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(a.ln_w[t] + c)), be = __ldg(reinterpret_cast<const float4*>(a.ln_b[t] + c));
+          st4_as<T>(xo + c, make_float4((f[i].x - mean) * rstd * g.x + be.x, (f[i].y - mean) * rstd * g.y + be.y,
+                                        (f[i].z - mean) * rstd * g.z + be.z, (f[i].w - mean) * rstd * g.w + be.w));
+        }
+      }
+    }
+  }
+}
+
+// dynamic smem: per warp [2 tasks][dgamma | dbeta][NV*128] fp32 partial sums (warp-private columns: no atomics)
+template <typename T, int NE, int NV>
+__global__ void __launch_bounds__(128, 2) head_bwd_reg_kernel(const HeadFusedDev a) {
+  constexpr int WARPS = 4, COLS = NV * 128;
+  extern __shared__ float4 acc_sm4[];
+  float* acc_sm = reinterpret_cast<float*>(acc_sm4);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* mine = acc_sm + wib * (4 * COLS);
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(mine + r * COLS + (i * 32 + lane) * 4) = make_float4(0, 0, 0, 0);
+  const int64_t warp0 = (int64_t)blockIdx.x * WARPS + wib, nw = (int64_t)gridDim.x * WARPS;
+  const int d = a.d;
+  const float inv_d = 1.f / (float)d, inv_n = 1.f / (float)NE;
+  for (int64_t b = warp0; b < a.B; b += nw) {
+    const float* evb = a.ev + b * (int64_t)NE * d;
+    float4 E[NE][NV];
+#pragma unroll
+    for (int k = 0; k < NE; ++k)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        E[k][i] = c < d ? __ldcs(reinterpret_cast<const float4*>(evb + k * d + c)) : make_float4(0, 0, 0, 0);
+      }
+    float wt[2][NE];
+    float4 df[2][NV];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+#pragma unroll
+      for (int k = 0; k < NE; ++k) wt[t][k] = a.w[((int64_t)t * a.B + b) * NE + k];
+      const float mean = a.stats[((int64_t)t * a.B + b) * 2], rstd = a.stats[((int64_t)t * a.B + b) * 2 + 1];
+      const T* dy = (const T*)a.dxn + ((int64_t)t * a.B + b) * d;
+      float4 dg[NV];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        float4 f = make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < NE; ++k) fma4(f, wt[t][k], E[k][i]);
+        dg[i] = make_float4(0, 0, 0, 0);
+        df[t][i] = make_float4(0, 0, 0, 0);
+        if (c < d) {
+          const float4 y = ld4_as<T>(dy + c);
+          const float4 g = __ldg(reinterpret_cast<const float4*>(a.ln_w[t] + c));
+          const float4 xh = make_float4((f.x - mean) * rstd, (f.y - mean) * rstd, (f.z - mean) * rstd, (f.w - mean) * rstd);
+          float4* pg = reinterpret_cast<float4*>(mine + (2 * t) * COLS + c);
+          float4* pb = reinterpret_cast<float4*>(mine + (2 * t + 1) * COLS + c);
+          float4 ag = *pg, ab = *pb;
+          ag.x = fmaf(y.x, xh.x, ag.x); ag.y = fmaf(y.y, xh.y, ag.y); ag.z = fmaf(y.z, xh.z, ag.z); ag.w = fmaf(y.w, xh.w, ag.w);
+          ab.x += y.x; ab.y += y.y; ab.z += y.z; ab.w += y.w;
+          *pg = ag; *pb = ab;
+          dg[i] = make_float4(y.x * g.x, y.y * g.y, y.z * g.z, y.w * g.w);
+          s1 += dg[i].x + dg[i].y + dg[i].z + dg[i].w;
+          s2 += dot4(dg[i], xh);
+          df[t][i] = xh;
+        }
+      }
+      s1 = warp_sum(s1) * inv_d; s2 = warp_sum(s2) * inv_d;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < d) {
+          df[t][i].x = rstd * (dg[i].x - s1 - df[t][i].x * s2);
+          df[t][i].y = rstd * (dg[i].y - s1 - df[t][i].y * s2);
+          df[t][i].z = rstd * (dg[i].z - s1 - df[t][i].z * s2);
+          df[t][i].w = rstd * (dg[i].w - s1 - df[t][i].w * s2);
+        }
+      }
+    }
+    // gate backward: dw_t[k] = <dfused_t, E_k>  (12 dot products reduced together)
+    float dw[2][NE];
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int k = 0; k < NE; ++k) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc += dot4(df[t][i], E[k][i]);
+        dw[t][k] = acc;
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int k = 0; k < NE; ++k) dw[t][k] += __shfl_xor_sync(0xffffffffu, dw[t][k], o);
+    // expert_vecs is dead from here on
+    float4 dq[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) dq[i] = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      float dot = 0.f;
+#pragma unroll
+      for (int k = 0; k < NE; ++k) dot += wt[t][k] * dw[t][k];
+      float sel = 0.f;
+#pragma unroll
+      for (int k = 0; k < NE; ++k) {
+        const float dlk = wt[t][k] * (dw[t][k] - dot);
+        sel = lane == k ? dlk : sel;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = (i * 32 + lane) * 4;
+          if (c < d) fma4(dq[i], dlk, __ldg(reinterpret_cast<const float4*>(a.wg[t] + k * d + c)));
+        }
+      }
+      if (lane < NE) a.dl[((int64_t)t * a.B + b) * NE + lane] = sel;
+    }
+    float* dev = a.d_ev + b * (int64_t)NE * d;
+#pragma unroll
+    for (int k = 0; k < NE; ++k)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < d) {
+          float4 v;
+          v.x = wt[0][k] * df[0][i].x + wt[1][k] * df[1][i].x + inv_n * dq[i].x;
+          v.y = wt[0][k] * df[0][i].y + wt[1][k] * df[1][i].y + inv_n * dq[i].y;
+          v.z = wt[0][k] * df[0][i].z + wt[1][k] * df[1][i].z + inv_n * dq[i].z;
+          v.w = wt[0][k] * df[0][i].w + wt[1][k] * df[1][i].w + inv_n * dq[i].w;
+          __stcs(reinterpret_cast<float4*>(dev + k * d + c), v);
+        }
+      }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 4 * COLS; idx += 128) {
+    const int r = idx / COLS, c = idx - r * COLS;
+    if (c < d) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) s += acc_sm[w * (4 * COLS) + idx];
+      atomicAdd(((r & 1) ? a.dbeta[r >> 1] : a.dgamma[r >> 1]) + c, s);
+    }
+  }
+}
+
 struct HeadSaved { void* query; float *w, *st; void *xn, *z1, *a1, *z2, *a2; };
 static HeadSaved head_layout(Arena& A, const mmoe_head_cfg& cfg, int B, int dtype) {
   HeadSaved s{};
@@ -365,9 +625,13 @@ static int head_fwd_t(const mmoe_call* c, const mmoe_head_cfg* cfg, const float*
   uint32_t k0, k1;
   {
     HeadFusedDev a = head_dev<T>(c, cfg, ev, s, ix);
-    if (d <= 768) head_mix_ln_fwd_kernel<T, 6><<<rows_grid(B, 8), 256, 0, st>>>(a);
+    if (n == 6 && d <= 768) {
+      int64_t blocks = ((int64_t)B + 3) / 4;
+      if (blocks > (int64_t)sm_count() * 2) blocks = (int64_t)sm_count() * 2;
+      head_fwd_reg_kernel<T, 6, 6><<<(int)blocks, 128, 0, st>>>(a);
+    } else if (d <= 768) head_mix_ln_fwd_kernel<T, 6><<<rows_grid(B, 8), 256, 0, st>>>(a);
     else head_mix_ln_fwd_kernel<T, 8><<<rows_grid(B, 8), 256, 0, st>>>(a);
-    MMOE_LAUNCH_OK("head_mix_ln_fwd_kernel");
+    MMOE_LAUNCH_OK("head forward mix/LN kernel");
     if (gate_w != nullptr) MMOE_CUDA(cudaMemcpyAsync(gate_w, s.w, (size_t)2 * B * n * 4, cudaMemcpyDeviceToDevice, st));
   }
   {
@@ -420,7 +684,7 @@ static int head_bwd_t(const mmoe_call* c, const mmoe_head_cfg* cfg, const float*
   uint32_t k0, k1;
   for (int k = 0; k < 2; ++k) {
     site_keys(c->seed, 20 + k, &k0, &k1);
-    gemv_bwd_kernel<T><<<rows_grid(B, 2), 256, 0, st>>>(dlogits + (size_t)k * B, (const T*)s.a2 + (size_t)k * B * h2,
+    gemv_bwd_kernel<T><<<rows_grid(B, 8), 256, 0, st>>>(dlogits + (size_t)k * B, (const T*)s.a2 + (size_t)k * B * h2,
                                                         (const T*)s.z2 + (size_t)k * B * h2, (const float*)P[ix.w3[k]],
                                                         (T*)t.dz2 + (size_t)k * B * h2, (float*)G[ix.w3[k]], (float*)G[ix.b3[k]],
                                                         (float*)G[ix.b2[k]], B, h2, thresh, scale, k0, k1);
@@ -458,9 +722,18 @@ static int head_bwd_t(const mmoe_call* c, const mmoe_head_cfg* cfg, const float*
     int64_t blocks = ((int64_t)B + 3) / 4;
     const int64_t cap = (int64_t)sm_count() * 4;
     if (blocks > cap) blocks = cap;
-    if (d <= 768) head_ln_mix_bwd_kernel<T, 6><<<(int)blocks, 128, 0, st>>>(a);
+    if (n == 6 && d <= 768) {
+      constexpr int SM_BYTES = 4 * 4 * 6 * 128 * 4;      // 48 KB: 4 warps x [2 tasks][dgamma|dbeta][768]
+      static bool attr = false;
+      if (!attr) {
+        MMOE_CUDA(cudaFuncSetAttribute(head_bwd_reg_kernel<T, 6, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BYTES));
+        attr = true;
+      }
+      if (blocks > (int64_t)sm_count() * 2) blocks = (int64_t)sm_count() * 2;
+      head_bwd_reg_kernel<T, 6, 6><<<(int)blocks, 128, SM_BYTES, st>>>(a);
+    } else if (d <= 768) head_ln_mix_bwd_kernel<T, 6><<<(int)blocks, 128, 0, st>>>(a);
     else head_ln_mix_bwd_kernel<T, 8><<<(int)blocks, 128, 0, st>>>(a);
-    MMOE_LAUNCH_OK("head_ln_mix_bwd_kernel");
+    MMOE_LAUNCH_OK("head backward LN/mix kernel");
   }
   for (int k = 0; k < 2; ++k)
     MMOE_TRY(small_wgrad(t.dl + (size_t)k * B * n, s.query, dtype, (float*)G[ix.gw[k]], (float*)G[ix.gb[k]], B, d, n, st));

@@ -207,11 +207,21 @@ static __global__ void __launch_bounds__(256) small_wgrad_kernel(const float* __
   float acc[MIX_MAXN], accb[MIX_MAXN];
 #pragma unroll
   for (int k = 0; k < MIX_MAXN; ++k) acc[k] = accb[k] = 0.f;
-  for (int64_t b = b0 + sub; b < b1; b += 4) {
-    const float x = c < d ? load_as_f(X, b * d + c, x_dtype) : 0.f;
+  // 4 rows per thread per trip: all of their loads are issued before the first FMA (the loop is latency-bound otherwise)
+  for (int64_t bb = b0 + sub; bb < b1; bb += 16) {
+    float x[4], cf[4][MIX_MAXN];
 #pragma unroll
-    for (int k = 0; k < MIX_MAXN; ++k)
-      if (k < n) { const float cf = coef[b * n + k]; acc[k] = fmaf(cf, x, acc[k]); accb[k] += cf; }
+    for (int u = 0; u < 4; ++u) {
+      const int64_t b = bb + 4 * u;
+      const bool ok = b < b1;
+      x[u] = (ok && c < d) ? load_as_f(X, b * d + c, x_dtype) : 0.f;
+#pragma unroll
+      for (int k = 0; k < MIX_MAXN; ++k) cf[u][k] = (ok && k < n) ? __ldg(coef + b * n + k) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int k = 0; k < MIX_MAXN; ++k) { acc[k] = fmaf(cf[u][k], x[u], acc[k]); accb[k] += cf[u][k]; }
   }
 #pragma unroll
   for (int k = 0; k < MIX_MAXN; ++k) red[sub][k][cl] = acc[k];
@@ -230,7 +240,7 @@ static __global__ void __launch_bounds__(256) small_wgrad_kernel(const float* __
 
 inline int small_wgrad(const float* coef, const void* X, int x_dtype, float* dW, float* db, int64_t B, int d, int n, cudaStream_t s) {
   int64_t chunks = (B + 255) / 256;
-  if (chunks > 64) chunks = 64;
+  if (chunks > 128) chunks = 128;
   if (chunks < 1) chunks = 1;
   const int64_t rpb = (B + chunks - 1) / chunks;
   dim3 grid((d + 63) / 64, (unsigned)chunks);
