@@ -223,7 +223,7 @@ constexpr int TMAX_STAGES = 6;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TEPI_WARP_BYTES = 4096;     // per-warp staging slab: 32 rows x 128 B
 constexpr int TEPI_BYTES = TC_EPI_WARPS * TEPI_WARP_BYTES;
-constexpr int TEPI_BIAS_BYTES = 2 * TBN * 4;   // per accumulator stage: the tile's 256 bias values (fast epilogue)
+constexpr int TEPI_BIAS_BYTES = TC_EPI_WARPS * 64 * 4;   // per epilogue warp: the 64 bias values of its current chunk (fast epilogue)
 constexpr int TBAR_BYTES = 256;              // 16 mbarriers + the TMEM base slot
 constexpr int TC_SMEM_BYTES = TC_PIPE_BYTES + TEPI_BYTES + TBAR_BYTES + TEPI_BIAS_BYTES;   // 231,680 B of the 232,448 B limit
 constexpr int TC_THREADS = 128 + 32 * TC_EPI_WARPS;
@@ -312,7 +312,7 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // TMA load issued by either CTA of the pair into ITS OWN shared memory, completing bytes on the leader's barrier
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
@@ -380,6 +380,58 @@ __device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int tile) {
   t.kb0 = t.split * g.kb_per_split;
   t.kb1 = min(g.kb_total, t.kb0 + g.kb_per_split);
   return t;
+}
+
+// Fast-epilogue math for one 64-column chunk of the thread's accumulator row, specialised at compile time so the unrolled
+// loop carries no per-element branches (the unspecialised loop cost ~1000 instructions per chunk with ReLU + dropout and
+// made the K = 768 GEMMs epilogue-bound).
+//   SCALED: the bias table already holds bias * dscale and the dropout scale is folded into one FFMA (act <= 1 only)
+//   DROP  : keyed-hash dropout; the pair index fits 32 bits (checked on the host), so the high-word term of drop_hash
+//           vanishes and the key mix is hoisted; keep tests are done on the raw 32-bit hash (no field extraction)
+template <int ACT, bool DROP, bool SCALED, bool BF16>
+__device__ __forceinline__ void epi_chunk_math(const uint32_t (&v)[64], const float* tab, uint32_t (&pk)[32], float dscale,
+                                               uint32_t thresh, uint32_t dk0, uint32_t dk1, uint32_t pair0) {
+  const uint32_t thi = thresh << 16;
+#pragma unroll
+  for (int j = 0; j < 64; j += 2) {
+    const float2 bb = *reinterpret_cast<const float2*>(tab + j);           // warp-uniform address: smem broadcast
+    float v0, v1;
+    if (SCALED) { v0 = fmaf(__uint_as_float(v[j]), dscale, bb.x); v1 = fmaf(__uint_as_float(v[j + 1]), dscale, bb.y); }
+    else { v0 = __uint_as_float(v[j]) + bb.x; v1 = __uint_as_float(v[j + 1]) + bb.y; }
+    if (ACT == 1) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+    else if (ACT == 2) { v0 = gelu_fast_f(v0); v1 = gelu_fast_f(v1); }
+    else if (ACT == 3) { v0 = sigmoid_f(v0); v1 = sigmoid_f(v1); }
+    if (DROP) {
+      uint32_t x = ((pair0 + (uint32_t)(j >> 1)) ^ dk0) * 0x9E3779B1u;     // == drop_hash(dk0, dk1, pair) for pair < 2^32
+      x ^= x >> 15; x *= 0x85EBCA77u;
+      x ^= x >> 13; x = (x ^ dk1) * 0xC2B2AE3Du;
+      x ^= x >> 16;
+      const bool k0 = (x << 16) >= thi, k1 = x >= thi;                     // low / high 16 bits >= thresh
+      if (SCALED) { v0 = k0 ? v0 : 0.f; v1 = k1 ? v1 : 0.f; }
+      else { v0 = k0 ? v0 * dscale : 0.f; v1 = k1 ? v1 * dscale : 0.f; }
+    }
+    pk[j >> 1] = BF16 ? pack_bf16(v0, v1) : pack_f16(v0, v1);
+  }
+}
+template <bool RICH, bool BF16>
+__device__ __forceinline__ void epi_chunk_dispatch(int act, bool drop, bool scaled, const uint32_t (&v)[64], const float* tab,
+                                                   uint32_t (&pk)[32], float dscale, uint32_t thresh, uint32_t dk0, uint32_t dk1,
+                                                   uint32_t pair0) {
+  if (act == 0) {
+    if (!drop) epi_chunk_math<0, false, false, BF16>(v, tab, pk, dscale, thresh, dk0, dk1, pair0);
+    else if (scaled) epi_chunk_math<0, true, true, BF16>(v, tab, pk, dscale, thresh, dk0, dk1, pair0);
+    else epi_chunk_math<0, true, false, BF16>(v, tab, pk, dscale, thresh, dk0, dk1, pair0);
+  } else if (act == 1) {
+    if (!drop) epi_chunk_math<1, false, false, BF16>(v, tab, pk, dscale, thresh, dk0, dk1, pair0);
+    else if (scaled) epi_chunk_math<1, true, true, BF16>(v, tab, pk, dscale, thresh, dk0, dk1, pair0);
+    else epi_chunk_math<1, true, false, BF16>(v, tab, pk, dscale, thresh, dk0, dk1, pair0);
+  } else if (RICH && act == 2) {
+    if (!drop) epi_chunk_math<2, false, false, BF16>(v, tab, pk, dscale, thresh, dk0, dk1, pair0);
+    else epi_chunk_math<2, true, false, BF16>(v, tab, pk, dscale, thresh, dk0, dk1, pair0);
+  } else if (RICH) {
+    if (!drop) epi_chunk_math<3, false, false, BF16>(v, tab, pk, dscale, thresh, dk0, dk1, pair0);
+    else epi_chunk_math<3, true, false, BF16>(v, tab, pk, dscale, thresh, dk0, dk1, pair0);
+  }
 }
 
 // BN: tile width (compile-time so the TMA issue loop and the instruction descriptor are constants — the pipeline is
@@ -570,42 +622,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         // registers, writes the 16-bit row into the 128B-swizzled slab and one lane issues a TMA store of the
         // 32 x 64 block (rows >= M and columns >= N are clipped by the tensor map: no predicates anywhere).
         const int64_t m = m0 + lane;
-        // the tile's bias values for this warp's 128 columns, staged once per tile in a table indexed by the accumulator
-        // stage (the 4 warps of a column half write identical values; a warp is never more than one tile ahead of
-        // another because stage reuse needs all 8 arrivals on tmem_empty)
-        float* tab = bias_tab + as * TBN + half * 128;
-        {
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          const int nn = n0 + half * 128 + lane * 4;
-          if (bias != nullptr) {
-            if (nn + 0 < N) bv.x = __ldg(bias + nn + 0);
-            if (nn + 1 < N) bv.y = __ldg(bias + nn + 1);
-            if (nn + 2 < N) bv.z = __ldg(bias + nn + 2);
-            if (nn + 3 < N) bv.w = __ldg(bias + nn + 3);
-          }
-          *reinterpret_cast<float4*>(tab + lane * 4) = bv;
-          __syncwarp();
-        }
+        // warp-private table with the 64 bias values of the current chunk (pre-multiplied by the dropout scale when that
+        // can be folded into the accumulator FFMA)
+        float* tab = bias_tab + ew * 64;
+        const bool has_pre = RICH && preact != nullptr;
+        const bool drop = thresh != 0u;
+        const bool scaled = drop && act <= 1 && !has_pre;
+        bool released = false;
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           const int col0 = half * 128 + c * 64;
           const int nb = n0 + col0;
           if (nb >= N || col0 >= BN) break;
+          const bool last = c == 1 || nb + 64 >= N || col0 + 64 >= BN;
+          float2 bv = make_float2(0.f, 0.f);
+          if (bias != nullptr) {
+            const int nn = nb + lane * 2;
+            if (nn < N) bv.x = __ldg(bias + nn);
+            if (nn + 1 < N) bv.y = __ldg(bias + nn + 1);
+            if (scaled) { bv.x *= dscale; bv.y *= dscale; }
+          }
           uint32_t v[64];
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * TBN + col0);
           tmem_ld32_nowait(taddr, v);
           tmem_ld32_nowait(taddr + 32, v + 32);
+          __syncwarp();                          // every lane is done reading the previous chunk's table
+          *reinterpret_cast<float2*>(tab + lane * 2) = bv;
           tmem_ld_wait();
-          uint32_t pk[32];
-          const uint64_t idx0 = (uint64_t)m * (uint64_t)N + (uint64_t)nb;     // even (N and nb are even)
-          if (RICH && preact != nullptr) {
-            // pre-activation copy (for the backward of GELU): same slab, its own TMA store, before the activated tile
-#pragma unroll
-            for (int j = 0; j < 64; j += 2) {
-              const float2 bb = *reinterpret_cast<const float2*>(tab + c * 64 + j);
-              const float v0 = __uint_as_float(v[j]) + bb.x, v1 = __uint_as_float(v[j + 1]) + bb.y;
-              pk[j >> 1] = is_bf16 ? pack_bf16(v0, v1) : pack_f16(v0, v1);
+          __syncwarp();
+          if (last) {
+            // the accumulator stage is in registers: hand it back to the MMA warp before the math and the stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CTAS == 2) mbar_arrive_cluster(map_to_cta(tempty_bar(as), 0u)); else mbar_arrive(tempty_bar(as));
             }
+            released = true;
+          }
+          uint32_t pk[32];
+          const uint32_t pair0 = (uint32_t)(((uint64_t)m * (uint64_t)N + (uint64_t)nb) >> 1);   // N and nb are even
+          if (has_pre) {
+            // pre-activation copy (for the backward of GELU): same slab, its own TMA store, before the activated tile
+            if (is_bf16) epi_chunk_math<0, false, false, true>(v, tab, pk, 1.f, 0u, 0u, 0u, 0u);
+            else epi_chunk_math<0, false, false, false>(v, tab, pk, 1.f, 0u, 0u, 0u, 0u);
             if (store_pending) {
               if (lane == 0) tma_store_wait_read();
               __syncwarp();
@@ -624,21 +683,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
             }
             store_pending = true;
           }
-#pragma unroll
-          for (int j = 0; j < 64; j += 2) {
-            const float2 bb = *reinterpret_cast<const float2*>(tab + c * 64 + j);   // warp-uniform address: smem broadcast
-            float v0 = __uint_as_float(v[j]) + bb.x;
-            float v1 = __uint_as_float(v[j + 1]) + bb.y;
-            if (act == 1) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-            else if (RICH && act == 2) { v0 = gelu_fast_f(v0); v1 = gelu_fast_f(v1); }
-            else if (RICH && act == 3) { v0 = sigmoid_f(v0); v1 = sigmoid_f(v1); }
-            if (thresh != 0u) {
-              const uint32_t h = drop_hash(dk0, dk1, (idx0 + j) >> 1);
-              v0 = ((h & 0xFFFFu) >= thresh) ? v0 * dscale : 0.f;
-              v1 = ((h >> 16) >= thresh) ? v1 * dscale : 0.f;
-            }
-            pk[j >> 1] = is_bf16 ? pack_bf16(v0, v1) : pack_f16(v0, v1);
-          }
+          if (is_bf16) epi_chunk_dispatch<RICH, true>(act, drop, scaled, v, tab, pk, dscale, thresh, dk0, dk1, pair0);
+          else epi_chunk_dispatch<RICH, false>(act, drop, scaled, v, tab, pk, dscale, thresh, dk0, dk1, pair0);
           if (store_pending) {                   // the previous TMA store must have finished reading the slab
             if (lane == 0) tma_store_wait_read();
             __syncwarp();
@@ -657,10 +703,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           }
           store_pending = true;
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (CTAS == 2) mbar_arrive_cluster(map_to_cta(tempty_bar(as), 0u)); else mbar_arrive(tempty_bar(as));
+        if (!released) {                         // this warp's column half lies outside the matrix
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CTAS == 2) mbar_arrive_cluster(map_to_cta(tempty_bar(as), 0u)); else mbar_arrive(tempty_bar(as));
+          }
         }
         if (++as == 2) { as = 0; aphase ^= 1u; }
         continue;
@@ -877,6 +925,7 @@ static int launch_tc(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream_t
                         e.residual == nullptr && e.colsum == nullptr && e.act >= 0 && e.act <= 3 && e.alpha == 1.0f &&
                         (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 && (e.ldo % 8) == 0 && q.k_splits <= 1 &&
                         (e.preact == nullptr || (reinterpret_cast<uintptr_t>(e.preact) & 15) == 0) &&
+                        (e.drop_p <= 0.f || (uint64_t)q.M * (uint64_t)q.N <= (1ull << 33)) &&
                         getenv("MMOE_DEBUG_GENERAL_EPILOGUE") == nullptr;
       g.kind = fast ? 1 : 0;
       if (fast) MMOE_TRY(make_tmap(&g.tma_out, e.out, dtype, q.M, q.N, e.ldo, 32));
