@@ -34,6 +34,10 @@ template <> __device__ __forceinline__ float4 load4<__half>(const __half* p) {
   const __half2 b = *reinterpret_cast<const __half2*>(&u.y);
   return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
 }
+// what a value becomes when stored as T and read back
+template <typename T> __device__ __forceinline__ float4 round4(float4 v) {
+  return make_float4(to_f<T>(from_f<T>(v.x)), to_f<T>(from_f<T>(v.y)), to_f<T>(from_f<T>(v.z)), to_f<T>(from_f<T>(v.w)));
+}
 template <typename T> __device__ __forceinline__ void store4(T* p, float4 v);
 template <> __device__ __forceinline__ void store4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
@@ -323,41 +327,61 @@ struct LnBwdDev {
   int64_t rows; int d;
 };
 
-// NV = float4 per lane (6 covers d <= 768).  128-thread blocks, up to 3 per SM: the kernel is a stream of long-latency row
-// loads, so resident warps (not arithmetic) set its speed.
+// NV = float4 per lane (6 covers d <= 768).  The kernel is a stream of long-latency row loads, so bytes in flight per SM set
+// its speed: every load of a row (x, dy and the residual gradient) is issued before the first use, and the per-column
+// partial sums (d gamma, d beta, bias gradient) live in warp-private shared memory instead of 72 registers, which lets
+// 3 blocks of 4 warps share an SM without spilling.
 template <typename DT_, typename XT, typename T, int NV>
 __global__ void __launch_bounds__(128, 3) ln_bwd_kernel(const LnBwdDev a) {
   constexpr int LN_NV = NV;
-  constexpr int WARPS = 4;
-  __shared__ float red[WARPS][NV * 128];
+  constexpr int WARPS = 4, COLS = NV * 128;
+  __shared__ __align__(16) float accs[WARPS][3][COLS];           // [warp][dgamma | dbeta | colsum][column]
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp0 = (int64_t)blockIdx.x * WARPS + wib;
   const int64_t nwarps = (int64_t)gridDim.x * WARPS;
   const int d = a.d;
   const float inv_d = 1.0f / (float)d;
-  float4 acc_g[LN_NV], acc_b[LN_NV], acc_c[LN_NV];
+  float* mine = &accs[wib][0][0];
 #pragma unroll
-  for (int i = 0; i < LN_NV; ++i) acc_g[i] = acc_b[i] = acc_c[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int i = 0; i < LN_NV; ++i) *reinterpret_cast<float4*>(mine + r * COLS + (i * 32 + lane) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   const DT_* dy = reinterpret_cast<const DT_*>(a.dy);
   const XT* x = reinterpret_cast<const XT*>(a.x);
   T* gout = reinterpret_cast<T*>(a.g_out);
+  const bool want_wb = a.dgamma != nullptr, want_g = gout != nullptr || a.g_colsum != nullptr;
   for (int64_t row = warp0; row < a.rows; row += nwarps) {
+    float4 xh[LN_NV], dg[LN_NV], rs[LN_NV];
+#pragma unroll
+    for (int i = 0; i < LN_NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      xh[i] = dg[i] = rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < d) {
+        xh[i] = load4<XT>(x + row * d + c);
+        dg[i] = load4<DT_>(dy + row * d + c);
+        if (a.dres != nullptr) rs[i] = load4<float>(a.dres + row * d + c);
+      }
+    }
     const float mean = a.stats[row * 2], rstd = a.stats[row * 2 + 1];
-    float4 xh[LN_NV], dg[LN_NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < LN_NV; ++i) {
       const int c = (i * 32 + lane) * 4;
       if (c < d) {
-        const float4 xv = load4<XT>(x + row * d + c);
-        const float4 dv = load4<DT_>(dy + row * d + c);
+        const float4 dv = dg[i];
         const float4 g = load4<float>(a.gamma + c);
-        xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+        xh[i] = make_float4((xh[i].x - mean) * rstd, (xh[i].y - mean) * rstd, (xh[i].z - mean) * rstd, (xh[i].w - mean) * rstd);
         dg[i] = make_float4(dv.x * g.x, dv.y * g.y, dv.z * g.z, dv.w * g.w);
         s1 += dg[i].x + dg[i].y + dg[i].z + dg[i].w;
         s2 += dg[i].x * xh[i].x + dg[i].y * xh[i].y + dg[i].z * xh[i].z + dg[i].w * xh[i].w;
-        acc_g[i].x += dv.x * xh[i].x; acc_g[i].y += dv.y * xh[i].y; acc_g[i].z += dv.z * xh[i].z; acc_g[i].w += dv.w * xh[i].w;
-        acc_b[i].x += dv.x; acc_b[i].y += dv.y; acc_b[i].z += dv.z; acc_b[i].w += dv.w;
+        if (want_wb) {
+          float4* pg = reinterpret_cast<float4*>(mine + c);
+          float4* pb = reinterpret_cast<float4*>(mine + COLS + c);
+          float4 ag = *pg, ab = *pb;
+          ag.x = fmaf(dv.x, xh[i].x, ag.x); ag.y = fmaf(dv.y, xh[i].y, ag.y); ag.z = fmaf(dv.z, xh[i].z, ag.z); ag.w = fmaf(dv.w, xh[i].w, ag.w);
+          ab.x += dv.x; ab.y += dv.y; ab.z += dv.z; ab.w += dv.w;
+          *pg = ag; *pb = ab;
+        }
       }
     }
     s1 = warp_sum(s1) * inv_d;
@@ -367,50 +391,44 @@ __global__ void __launch_bounds__(128, 3) ln_bwd_kernel(const LnBwdDev a) {
       const int c = (i * 32 + lane) * 4;
       if (c < d) {
         float4 o;
-        o.x = rstd * (dg[i].x - s1 - xh[i].x * s2);
-        o.y = rstd * (dg[i].y - s1 - xh[i].y * s2);
-        o.z = rstd * (dg[i].z - s1 - xh[i].z * s2);
-        o.w = rstd * (dg[i].w - s1 - xh[i].w * s2);
-        if (a.dres != nullptr) {
-          const float4 r = load4<float>(a.dres + row * d + c);
-          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-        }
+        o.x = rstd * (dg[i].x - s1 - xh[i].x * s2) + rs[i].x;
+        o.y = rstd * (dg[i].y - s1 - xh[i].y * s2) + rs[i].y;
+        o.z = rstd * (dg[i].z - s1 - xh[i].z * s2) + rs[i].z;
+        o.w = rstd * (dg[i].w - s1 - xh[i].w * s2) + rs[i].w;
         if (a.dx != nullptr) store4<float>(a.dx + row * d + c, o);
-        if (gout != nullptr || a.g_colsum != nullptr) {
+        if (want_g) {
           if (a.thresh != 0) {
-            const uint64_t idx = (uint64_t)row * d + c;
-            o.x = drop_keep(a.k0, a.k1, idx + 0, a.thresh) ? o.x * a.scale : 0.f;
-            o.y = drop_keep(a.k0, a.k1, idx + 1, a.thresh) ? o.y * a.scale : 0.f;
-            o.z = drop_keep(a.k0, a.k1, idx + 2, a.thresh) ? o.z * a.scale : 0.f;
-            o.w = drop_keep(a.k0, a.k1, idx + 3, a.thresh) ? o.w * a.scale : 0.f;
+            const uint64_t idx = (uint64_t)row * d + c;                   // multiple of 4: two hash pairs
+            const uint32_t h0 = drop_hash(a.k0, a.k1, idx >> 1), h1 = drop_hash(a.k0, a.k1, (idx >> 1) + 1);
+            o.x = ((h0 & 0xFFFFu) >= a.thresh) ? o.x * a.scale : 0.f;
+            o.y = ((h0 >> 16) >= a.thresh) ? o.y * a.scale : 0.f;
+            o.z = ((h1 & 0xFFFFu) >= a.thresh) ? o.z * a.scale : 0.f;
+            o.w = ((h1 >> 16) >= a.thresh) ? o.w * a.scale : 0.f;
           }
           if (gout != nullptr) {
             store4<T>(gout + row * d + c, o);
-            o = load4<T>(gout + row * d + c);
+            o = round4<T>(o);                                             // the bias gradient sums what was stored
           }
-          acc_c[i].x += o.x; acc_c[i].y += o.y; acc_c[i].z += o.z; acc_c[i].w += o.w;
+          float4* pc = reinterpret_cast<float4*>(mine + 2 * COLS + c);
+          float4 ac = *pc;
+          ac.x += o.x; ac.y += o.y; ac.z += o.z; ac.w += o.w;
+          *pc = ac;
         }
       }
     }
   }
-  // block reduction of the per-lane column partials, then one atomic per column per block
-  auto reduce_to = [&](float4 (&acc)[LN_NV], float* dst) {
-#pragma unroll
-    for (int i = 0; i < LN_NV; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      if (c < d) *reinterpret_cast<float4*>(&red[wib][c]) = acc[i];
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < d; c += 128) {
+  __syncthreads();
+  // block reduction of the warp-private column partials, then one atomic per column per block
+  for (int idx = threadIdx.x; idx < 3 * COLS; idx += 128) {
+    const int r = idx / COLS, c = idx - r * COLS;
+    float* dst = r == 0 ? a.dgamma : (r == 1 ? a.dbeta : a.g_colsum);
+    if (c < d && dst != nullptr && (r == 2 ? want_g : want_wb)) {
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < WARPS; ++w) t += red[w][c];
+      for (int w = 0; w < WARPS; ++w) t += accs[w][r][c];
       atomicAdd(dst + c, t);
     }
-    __syncthreads();
-  };
-  if (a.dgamma != nullptr) { reduce_to(acc_g, a.dgamma); reduce_to(acc_b, a.dbeta); }
-  if (a.g_colsum != nullptr) reduce_to(acc_c, a.g_colsum);
+  }
 }
 
 template <typename T, int NV>
@@ -439,7 +457,7 @@ int layernorm_bwd(const LnBwdArgs& a, cudaStream_t s) {
   dev.scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
   dev.k0 = a.k0; dev.k1 = a.k1; dev.rows = a.rows; dev.d = a.d;
   int64_t blocks = (a.rows + 3) / 4;
-  const int64_t cap = (int64_t)sm_count() * 6;
+  const int64_t cap = (int64_t)sm_count() * 3;      // resident blocks: 3 per SM
   if (blocks > cap) blocks = cap;
   MMOE_CHECK((a.dy_dtype == MMOE_F32 || a.dy_dtype == a.dtype) && (a.x_dtype == MMOE_F32 || a.x_dtype == a.dtype),
              "layernorm_bwd: dy and x must be fp32 or the operand dtype");
