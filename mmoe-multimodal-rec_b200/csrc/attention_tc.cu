@@ -40,20 +40,19 @@ template <> struct MmaT<__half> {
 // A (16 x 16) from memory [m][k], k contiguous
 template <typename T>
 __device__ __forceinline__ void frag_a_mk(uint32_t (&a)[4], const T* base, int pitch, int m0, int k0, int lane) {
-  const int g = lane >> 2, t = lane & 3;
-  const T* p = base + (m0 + g) * pitch + k0 + 2 * t;
-  a[0] = *reinterpret_cast<const uint32_t*>(p);
-  a[1] = *reinterpret_cast<const uint32_t*>(p + 8 * pitch);
-  a[2] = *reinterpret_cast<const uint32_t*>(p + 8);
-  a[3] = *reinterpret_cast<const uint32_t*>(p + 8 * pitch + 8);
+  // four 8x8 blocks: a0 = (m 0-7, k 0-7)  a1 = (m 8-15, k 0-7)  a2 = (m 0-7, k 8-15)  a3 = (m 8-15, k 8-15)
+  const int mat = lane >> 3, r = lane & 7;
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(base + (m0 + 8 * (mat & 1) + r) * pitch + k0 + 8 * (mat >> 1));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr));
 }
-// B (16 k x 8 n) from memory [n][k], k contiguous
+// B fragments of TWO adjacent 8-key tiles (n0..n0+7 and n0+8..n0+15) from memory [n][k], k contiguous
 template <typename T>
-__device__ __forceinline__ void frag_b_nk(uint32_t (&b)[2], const T* base, int pitch, int n0, int k0, int lane) {
-  const int g = lane >> 2, t = lane & 3;
-  const T* p = base + (n0 + g) * pitch + k0 + 2 * t;
-  b[0] = *reinterpret_cast<const uint32_t*>(p);
-  b[1] = *reinterpret_cast<const uint32_t*>(p + 8);
+__device__ __forceinline__ void frag_b_nk2(uint32_t (&b0)[2], uint32_t (&b1)[2], const T* base, int pitch, int n0, int k0, int lane) {
+  const int mat = lane >> 3, r = lane & 7;
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(base + (n0 + 8 * (mat >> 1) + r) * pitch + k0 + 8 * (mat & 1));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(b0[0]), "=r"(b0[1]), "=r"(b1[0]), "=r"(b1[1]) : "r"(addr));
 }
 // B (16 k x 8 n) from memory [k][n], n contiguous: two 8x8 blocks (k 0-7, k 8-15), transposed on load
 template <typename T>
@@ -74,16 +73,24 @@ __device__ __forceinline__ void frag_a_km(uint32_t (&a)[4], const T* base, int p
 // global [rows][HD] (row stride ld) -> smem [64][PITCH]; rows >= valid are zero-filled.  Asynchronous 16-byte copies
 // (cp.async, LDGSTS): every thread puts all of its chunks in flight before anyone waits, so a tile costs one memory
 // latency instead of one per chunk.
+// A half-warp owns a row (lanes 0..CH-1 of the half carry its 16-byte chunks), so addresses advance by a constant per
+// trip: the previous element-indexed loop spent a fifth of the backward kernel's instructions on div/mod address math.
 template <typename T, int HD>
 __device__ __forceinline__ void stage_tile(T* dst, const T* src, int64_t ld, int valid, int rows_padded, int nthreads) {
   constexpr int PITCH = HD + 8, CH = HD / 8;
-  for (int e = threadIdx.x; e < rows_padded * CH; e += nthreads) {
-    const int r = e / CH, c = (e - r * CH) * 8;
+  static_assert(CH <= 16, "a row must fit a half-warp of 16-byte chunks");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = nthreads >> 5;
+  const int ch = lane & 15;
+  if (ch >= CH) return;
+  int r = 2 * warp + (lane >> 4);
+  const T* g = src + (int64_t)r * ld + ch * 8;
+  uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + r * PITCH + ch * 8);
+  const int64_t gstep = (int64_t)2 * nw * ld;
+  const uint32_t dstep = (uint32_t)(2 * nw * PITCH * sizeof(T));
+  for (; r < rows_padded; r += 2 * nw, g += gstep, d += dstep) {
     const bool ok = r < valid;
-    const T* g = ok ? src + (int64_t)r * ld + c : src;
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + r * PITCH + c);
     const int bytes = ok ? 16 : 0;           // src-size 0 -> the 16 destination bytes are zero-filled
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(g), "r"(bytes) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(ok ? g : src), "r"(bytes) : "memory");
   }
 }
 __device__ __forceinline__ void stage_wait() {
@@ -173,11 +180,12 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcDev a) {
     uint32_t af[4];
     frag_a_mk<T>(af, Qs, PITCH, row0, kk * 16, lane);
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      if (nt < NT) {
-        uint32_t bf[2];
-        frag_b_nk<T>(bf, Ks, PITCH, nt * 8, kk * 16, lane);
-        MmaT<T>::mma(s[nt], af, bf);
+    for (int nt = 0; nt < 8; nt += 2) {
+      if (nt < NT) {                   // an odd NT reads one zero-filled key tile too many (rows < krows are staged)
+        uint32_t b0[2], b1[2];
+        frag_b_nk2<T>(b0, b1, Ks, PITCH, nt * 8, kk * 16, lane);
+        MmaT<T>::mma(s[nt], af, b0);
+        MmaT<T>::mma(s[nt + 1], af, b1);
       }
     }
   }
@@ -234,7 +242,8 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcDev a) {
   }
 }
 
-// column sums of a warp's 16 x (HD) accumulator slab -> smem partials
+// column sums of a warp's 16 x (HD) accumulator slab -> this warp's private row of partials (plain stores: a float
+// atomicAdd on shared memory is a CAS loop, and four warps contending on it cost a quarter of the kernel)
 template <int HD>
 __device__ __forceinline__ void colsum_to_smem(const float (&acc)[HD / 8][4], float* dst, int lane) {
   const int g = lane >> 2, t = lane & 3;
@@ -243,7 +252,7 @@ __device__ __forceinline__ void colsum_to_smem(const float (&acc)[HD / 8][4], fl
     float c0 = acc[nt][0] + acc[nt][2], c1 = acc[nt][1] + acc[nt][3];
 #pragma unroll
     for (int o = 4; o < 32; o <<= 1) { c0 += __shfl_xor_sync(0xffffffffu, c0, o); c1 += __shfl_xor_sync(0xffffffffu, c1, o); }
-    if (g == 0) { atomicAdd(dst + nt * 8 + 2 * t, c0); atomicAdd(dst + nt * 8 + 2 * t + 1, c1); }
+    if (g == 0) *reinterpret_cast<float2*>(dst + nt * 8 + 2 * t) = make_float2(c0, c1);
   }
 }
 
@@ -255,9 +264,9 @@ __global__ void __launch_bounds__(128) attn_tc_bwd_kernel(const AttnTcDev a) {
   T* Ks = Qs + 64 * PITCH;
   T* Vs = Ks + 64 * PITCH;
   T* dOs = Vs + 64 * PITCH;
-  T* Ps = dOs + 64 * PITCH;        // probabilities after dropout, [query][key]
-  T* dSs = Ps + 64 * PP;           // qscale * dS, [query][key]
-  float* bg = reinterpret_cast<float*>(dSs + 64 * PP);   // [3][HD]
+  T* Ps = Vs;                      // probabilities after dropout, [query][key]: takes over V's tile once S and dP exist
+  T* dSs = dOs + 64 * PITCH;       // qscale * dS, [query][key]
+  float* bg = reinterpret_cast<float*>(dSs + 64 * PP);   // [4 warps][3][HD] warp-private column-sum partials
   const int b = blockIdx.x / a.H, h = blockIdx.x - b * a.H;
   const int Sq = a.Sq, Sk = a.Sk;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -270,35 +279,42 @@ __global__ void __launch_bounds__(128) attn_tc_bwd_kernel(const AttnTcDev a) {
   stage_tile<T, HD>(dOs, (const T*)a.ctx + (int64_t)b * Sq * a.ldc + h * HD, a.ldc, Sq, qrows, blockDim.x);
   __shared__ uint8_t smask[64];
   if (a.mask != nullptr && threadIdx.x < Sk) smask[threadIdx.x] = a.mask[(int64_t)b * Sk + threadIdx.x];
-  for (int e = threadIdx.x; e < 3 * HD; e += blockDim.x) bg[e] = 0.f;
-  // zero the score tiles so that padded rows / keys read as exact zeros in phase 2
-  for (int e = threadIdx.x; e < 64 * PP / 2; e += blockDim.x) {
-    reinterpret_cast<uint32_t*>(Ps)[e] = 0u;
-    reinterpret_cast<uint32_t*>(dSs)[e] = 0u;
-  }
+  for (int e = threadIdx.x; e < 4 * 3 * HD; e += blockDim.x) bg[e] = 0.f;
+  // keys between Sk rounded up to 8 and Sk rounded up to 16 are written by nobody: zero them for phase 2
+  const bool zero_scores = NT * 8 != krows;
+  if (zero_scores)
+    for (int e = threadIdx.x; e < 64 * PP / 2; e += blockDim.x) reinterpret_cast<uint32_t*>(dSs)[e] = 0u;
   stage_wait();
   __syncthreads();
   const int row0 = warp * 16;
-  if (row0 < Sq) {
-    float s[8][4], dp[8][4];
+  float s[8][4], dp[8][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f; }
+  for (int nt = 0; nt < 8; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f; }
+  if (row0 < Sq) {
 #pragma unroll
     for (int kk = 0; kk < HD / 16; ++kk) {
       uint32_t aq[4], ad[4];
       frag_a_mk<T>(aq, Qs, PITCH, row0, kk * 16, lane);
       frag_a_mk<T>(ad, dOs, PITCH, row0, kk * 16, lane);
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        if (nt < NT) {
-          uint32_t bk[2], bv[2];
-          frag_b_nk<T>(bk, Ks, PITCH, nt * 8, kk * 16, lane);
-          frag_b_nk<T>(bv, Vs, PITCH, nt * 8, kk * 16, lane);
-          MmaT<T>::mma(s[nt], aq, bk);      // S  = Q K^T
-          MmaT<T>::mma(dp[nt], ad, bv);     // dP = dO V^T
+      for (int nt = 0; nt < 8; nt += 2) {
+        if (nt < NT) {               // an odd NT reads one zero-filled key tile too many (rows < krows are staged)
+          uint32_t bk0[2], bk1[2], bv0[2], bv1[2];
+          frag_b_nk2<T>(bk0, bk1, Ks, PITCH, nt * 8, kk * 16, lane);
+          frag_b_nk2<T>(bv0, bv1, Vs, PITCH, nt * 8, kk * 16, lane);
+          MmaT<T>::mma(s[nt], aq, bk0);      // S  = Q K^T
+          MmaT<T>::mma(dp[nt], ad, bv0);     // dP = dO V^T
+          MmaT<T>::mma(s[nt + 1], aq, bk1);
+          MmaT<T>::mma(dp[nt + 1], ad, bv1);
         }
       }
     }
+  }
+  __syncthreads();                   // every warp is done with V: its tile becomes P
+  if (zero_scores)
+    for (int e = threadIdx.x; e < 64 * PP / 2; e += blockDim.x) reinterpret_cast<uint32_t*>(Ps)[e] = 0u;
+  if (zero_scores) __syncthreads();
+  if (row0 < Sq) {
     softmax_frag(s, NT, Sk, a.mask ? smask : nullptr, a.qscale, lane);
     // dropout on P and dP, delta = sum_j P * dP, dS = P * (dP - delta)
     const uint64_t base = (uint64_t)blockIdx.x * Sq * Sk;
@@ -373,16 +389,19 @@ __global__ void __launch_bounds__(128) attn_tc_bwd_kernel(const AttnTcDev a) {
         }
       }
     }
-    T* dqo = (T*)a.dq + (int64_t)b * Sq * a.ldq + h * HD;
+    {
+      const bool ok0 = row0 + g < Sq, ok1 = row0 + g + 8 < Sq;
+      T* r0p = (T*)a.dq + ((int64_t)b * Sq + row0 + g) * a.ldq + h * HD + 2 * t;
+      T* r1p = r0p + 8 * a.ldq;
 #pragma unroll
-    for (int nt = 0; nt < HD / 8; ++nt) {
-      const int col = nt * 8 + 2 * t;
-      if (row0 + g < Sq) *reinterpret_cast<uint32_t*>(dqo + (int64_t)(row0 + g) * a.ldq + col) = MmaT<T>::pack(dq[nt][0], dq[nt][1]);
-      else { dq[nt][0] = dq[nt][1] = 0.f; }
-      if (row0 + g + 8 < Sq) *reinterpret_cast<uint32_t*>(dqo + (int64_t)(row0 + g + 8) * a.ldq + col) = MmaT<T>::pack(dq[nt][2], dq[nt][3]);
-      else { dq[nt][2] = dq[nt][3] = 0.f; }
+      for (int nt = 0; nt < HD / 8; ++nt) {
+        if (ok0) *reinterpret_cast<uint32_t*>(r0p + nt * 8) = MmaT<T>::pack(dq[nt][0], dq[nt][1]);
+        else { dq[nt][0] = dq[nt][1] = 0.f; }
+        if (ok1) *reinterpret_cast<uint32_t*>(r1p + nt * 8) = MmaT<T>::pack(dq[nt][2], dq[nt][3]);
+        else { dq[nt][2] = dq[nt][3] = 0.f; }
+      }
     }
-    if (a.bgq != nullptr) colsum_to_smem<HD>(dq, bg, lane);
+    if (a.bgq != nullptr) colsum_to_smem<HD>(dq, bg + warp * 3 * HD, lane);
   }
   __syncthreads();
   // phase 2: warp w owns keys [16w, 16w+16):  dV = Pd^T dO,  dK = (qscale dS)^T Q
@@ -407,28 +426,34 @@ __global__ void __launch_bounds__(128) attn_tc_bwd_kernel(const AttnTcDev a) {
         }
       }
     }
-    T* dko = (T*)a.dk + (int64_t)b * Sk * a.ldk + h * HD;
-    T* dvo = (T*)a.dv + (int64_t)b * Sk * a.ldv + h * HD;
+    {
+      const bool ok0 = key0 + g < Sk, ok1 = key0 + g + 8 < Sk;
+      T* k0p = (T*)a.dk + ((int64_t)b * Sk + key0 + g) * a.ldk + h * HD + 2 * t;
+      T* k1p = k0p + 8 * a.ldk;
+      T* v0p = (T*)a.dv + ((int64_t)b * Sk + key0 + g) * a.ldv + h * HD + 2 * t;
+      T* v1p = v0p + 8 * a.ldv;
 #pragma unroll
-    for (int nt = 0; nt < HD / 8; ++nt) {
-      const int col = nt * 8 + 2 * t;
-      if (key0 + g < Sk) {
-        *reinterpret_cast<uint32_t*>(dko + (int64_t)(key0 + g) * a.ldk + col) = MmaT<T>::pack(dk[nt][0], dk[nt][1]);
-        *reinterpret_cast<uint32_t*>(dvo + (int64_t)(key0 + g) * a.ldv + col) = MmaT<T>::pack(dv[nt][0], dv[nt][1]);
-      } else { dk[nt][0] = dk[nt][1] = dv[nt][0] = dv[nt][1] = 0.f; }
-      if (key0 + g + 8 < Sk) {
-        *reinterpret_cast<uint32_t*>(dko + (int64_t)(key0 + g + 8) * a.ldk + col) = MmaT<T>::pack(dk[nt][2], dk[nt][3]);
-        *reinterpret_cast<uint32_t*>(dvo + (int64_t)(key0 + g + 8) * a.ldv + col) = MmaT<T>::pack(dv[nt][2], dv[nt][3]);
-      } else { dk[nt][2] = dk[nt][3] = dv[nt][2] = dv[nt][3] = 0.f; }
+      for (int nt = 0; nt < HD / 8; ++nt) {
+        if (ok0) {
+          *reinterpret_cast<uint32_t*>(k0p + nt * 8) = MmaT<T>::pack(dk[nt][0], dk[nt][1]);
+          *reinterpret_cast<uint32_t*>(v0p + nt * 8) = MmaT<T>::pack(dv[nt][0], dv[nt][1]);
+        } else { dk[nt][0] = dk[nt][1] = dv[nt][0] = dv[nt][1] = 0.f; }
+        if (ok1) {
+          *reinterpret_cast<uint32_t*>(k1p + nt * 8) = MmaT<T>::pack(dk[nt][2], dk[nt][3]);
+          *reinterpret_cast<uint32_t*>(v1p + nt * 8) = MmaT<T>::pack(dv[nt][2], dv[nt][3]);
+        } else { dk[nt][2] = dk[nt][3] = dv[nt][2] = dv[nt][3] = 0.f; }
+      }
     }
-    if (a.bgk != nullptr) colsum_to_smem<HD>(dk, bg + HD, lane);
-    if (a.bgv != nullptr) colsum_to_smem<HD>(dv, bg + 2 * HD, lane);
+    if (a.bgk != nullptr) colsum_to_smem<HD>(dk, bg + warp * 3 * HD + HD, lane);
+    if (a.bgv != nullptr) colsum_to_smem<HD>(dv, bg + warp * 3 * HD + 2 * HD, lane);
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < HD; c += blockDim.x) {
-    if (a.bgq != nullptr) atomicAdd(a.bgq + h * HD + c, bg[c]);
-    if (a.bgk != nullptr) atomicAdd(a.bgk + h * HD + c, bg[HD + c]);
-    if (a.bgv != nullptr) atomicAdd(a.bgv + h * HD + c, bg[2 * HD + c]);
+  for (int c = threadIdx.x; c < 3 * HD; c += blockDim.x) {
+    float* dst = c < HD ? a.bgq : (c < 2 * HD ? a.bgk : a.bgv);
+    if (dst != nullptr) {
+      const float v = bg[c] + bg[3 * HD + c] + bg[6 * HD + c] + bg[9 * HD + c];
+      atomicAdd(dst + h * HD + (c % HD), v);
+    }
   }
 }
 
@@ -466,7 +491,7 @@ static int launch_tc(const AttnArgs& a, bool bwd, cudaStream_t s) {
     attn_tc_fwd_kernel<T, HD><<<a.B * a.H, threads, smem, s>>>(d);
     MMOE_LAUNCH_OK("attn_tc_fwd_kernel");
   } else {
-    const size_t smem = (size_t)4 * 64 * (HD + 8) * sizeof(T) + (size_t)2 * 64 * 72 * sizeof(T) + 3 * HD * sizeof(float);
+    const size_t smem = (size_t)4 * 64 * (HD + 8) * sizeof(T) + (size_t)64 * 72 * sizeof(T) + 4 * 3 * HD * sizeof(float);
     static bool cfg = false;
     if (!cfg) { MMOE_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<T, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
     attn_tc_bwd_kernel<T, HD><<<a.B * a.H, threads, smem, s>>>(d);
