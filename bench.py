@@ -219,6 +219,9 @@ def workload_config(B, n_gpus):
 
 
 # ----------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -254,6 +257,12 @@ def main():
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line
+        # NCCL still prints its version banner on fd 1: point fd 1 at stderr for the life of the process and keep a
+        # private duplicate of the real stdout for the JSON line
+        global _REAL_STDOUT
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         # ~280 MB of gradients per step overlap ~8 ms of backward: a few NCCL CTAs are plenty, and every SM NCCL holds
         # is an SM the persistent GEMM cannot use while it runs
         if args.nccl_ctas > 0:
@@ -383,9 +392,15 @@ def main():
     for j in range(2):
         done[j].record(cur)
 
+    loss_host = torch.empty(max(args.steps, 3), dtype=torch.float32).pin_memory()
+
     def e2e_loop(n):
+        """Every step: its batch comes from pinned host memory (copied on the side stream while the previous step
+        computes) and its loss is copied back to pinned host memory and READ by the host — one step late, while the next
+        step is already enqueued, the way a training loop logs its loss without draining the device every step."""
         prefetch(0, host[0])
         last = None
+        landed = [torch.cuda.Event() for _ in range(n)]
         for i in range(n):
             j = i & 1
             if i + 1 < n:
@@ -395,7 +410,13 @@ def main():
                 v.record_stream(cur)
             l = step(slots[j])
             done[j].record(cur)
-            last = float(l.item())          # device -> host read of the step's result
+            loss_host[i:i + 1].copy_(l.detach().reshape(1), non_blocking=True)      # device -> host read of the step's result
+            landed[i].record(cur)
+            if i >= 1:
+                landed[i - 1].synchronize()
+                last = float(loss_host[i - 1])
+        landed[n - 1].synchronize()
+        last = float(loss_host[n - 1])
         return last
 
     e2e_loop(3)
@@ -427,7 +448,7 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload_config(B, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(host[0]), "d2h_bytes_per_step": 4,
-                    "note": "pinned host batch copied on a side stream (double buffered) every step; loss.item() read back every step"},
+                    "note": "pinned host batch copied on a side stream (double buffered) every step; every step's loss copied to pinned host memory and read by the host one step later"},
             "gpu_launches": launches,
             "host_enqueue_ms_per_step": host_ms_step,
             "ms_per_step_min_median_max": [per_step[0], per_step[len(per_step) // 2], per_step[-1]], "slowest_step": slowest_step,
@@ -452,7 +473,7 @@ def main():
                                                   f"fwd+bwd, 2 timed steps ({ms_cpu:.0f} ms/step)"}
             except Exception as ex:  # noqa: BLE001
                 line["cpu_baseline"] = {"error": repr(ex)}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), flush=True, file=_REAL_STDOUT or sys.stdout)
     if distributed:
         dist.destroy_process_group()
 
