@@ -101,7 +101,9 @@ inline int wgrad_splits(int M, int N, int K) {
   const int tiles = ((M + 127) / 128) * ((N + 255) / 256);
   const int kb = (K + 63) / 64;
   int ks = (2 * sm_count() + tiles - 1) / tiles;
-  const int max_ks = kb / 4 > 1 ? kb / 4 : 1;
+  // every split adds M*N fp32 atomics (the L2 retires ~0.2 T atomics/s: a 3072x768 gradient costs ~13 us per split), so a
+  // split must carry at least 8 K-blocks of MMA work
+  const int max_ks = kb / 8 > 1 ? kb / 8 : 1;
   if (ks > max_ks) ks = max_ks;
   return ks < 1 ? 1 : ks;
 }

@@ -14,6 +14,7 @@
 // transpose bits), so forward, dgrad and wgrad need no transposed copies.
 #include <cuda.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 #include <mutex>
@@ -909,9 +910,20 @@ static int launch_tc(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream_t
   const int tile_m = TBM * ctas;
   int tiles = 0;
   bool rich = false;
-  for (int i = 0; i < n; ++i) {
-    TcGroup& g = P.g[i];
-    const mmoe_gemm_problem& q = pr[i];
+  // longest tiles first: the persistent tile list is walked in group order, and a split-K weight-gradient tile (hundreds
+  // of K-blocks) started last would leave the other SMs idle while it finishes
+  int order[kMaxGroups];
+  for (int i = 0; i < n; ++i) order[i] = i;
+  auto tile_kb = [&](int i) {
+    const int kb = (pr[i].K + TBK - 1) / TBK;
+    int ks = pr[i].k_splits < 1 ? 1 : pr[i].k_splits;
+    if (ks > kb) ks = kb;
+    return (kb + ks - 1) / ks;
+  };
+  std::stable_sort(order, order + n, [&](int a, int b) { return tile_kb(a) > tile_kb(b); });
+  for (int oi = 0; oi < n; ++oi) {
+    TcGroup& g = P.g[oi];
+    const mmoe_gemm_problem& q = pr[order[oi]];
     g.M = q.M; g.N = q.N; g.K = q.K;
     g.a_major = q.a_major; g.b_major = q.b_major;
     if (q.a_major == 0) MMOE_TRY(make_tmap(&g.tma_a, q.a, dtype, q.M, q.K, q.lda, TBM));
