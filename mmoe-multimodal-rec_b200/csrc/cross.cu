@@ -192,6 +192,7 @@ static CrossSaved cross_layout(Arena& A, const mmoe_cross_cfg& cfg, int B, int d
 struct CrossScratch {
   EncScratch enc;
   float *dU, *dI, *dpooled, *dnormed; void *dC, *dctx, *dq, *dkv, *g, *dz;
+  void *hand_u, *hand_i;       // EncHandoff buffers of the user / item stack (separate: the two stacks' stage calls may interleave)
 };
 static CrossScratch cross_scratch_layout(Arena& A, const mmoe_cross_cfg& cfg, int B, int dtype) {
   CrossScratch t{};
@@ -201,6 +202,7 @@ static CrossScratch cross_scratch_layout(Arena& A, const mmoe_cross_cfg& cfg, in
   t.dpooled = (float*)A.take((size_t)B * d * 4); t.dnormed = (float*)A.take((size_t)B * d * 4);
   t.dC = A.take(M * d * es); t.dctx = A.take(M * d * es); t.dq = A.take(M * d * es); t.dkv = A.take(M * 2 * d * es);
   t.g = A.take((size_t)B * d * es); t.dz = A.take((size_t)B * ff * es);
+  t.hand_u = A.take(M * d * es); t.hand_i = A.take(M * d * es);
   return t;
 }
 
@@ -450,15 +452,17 @@ extern "C" int mmoe_cross_bwd_stage(const mmoe_call* c, const mmoe_cross_cfg* cf
     if (!(stage == -1 || stage == 200 + l)) continue;
     ec.mask = item_mask; ec.site0 = 16 * l + 8;
     const float* x_in = l == 0 ? item : s.item[l].x_sum;
+    EncHandoff below{t.hand_i, l > 0 ? enc_g(G + ix.item0 + 12 * (l - 1)).b2 : nullptr, (uint32_t)(16 * (l - 1) + 8)};
     MMOE_TRY(enc_bwd(ec, enc_w(P + ix.item0 + 12 * l), enc_g(G + ix.item0 + 12 * l), x_in, s.item[l], t.enc, t.dI,
-                     l == 0 ? d_item : t.dI));
+                     l == 0 ? d_item : t.dI, l < cfg->n_layer - 1 ? t.hand_i : nullptr, l > 0 ? &below : nullptr));
   }
   for (int l = cfg->n_layer - 1; l >= 0; --l) {
     if (!(stage == -1 || stage == 100 + l)) continue;
     ec.mask = user_mask; ec.site0 = 16 * l;
     const float* x_in = l == 0 ? user : s.user[l].x_sum;
+    EncHandoff below{t.hand_u, l > 0 ? enc_g(G + ix.user0 + 12 * (l - 1)).b2 : nullptr, (uint32_t)(16 * (l - 1))};
     MMOE_TRY(enc_bwd(ec, enc_w(P + ix.user0 + 12 * l), enc_g(G + ix.user0 + 12 * l), x_in, s.user[l], t.enc, t.dU,
-                     l == 0 ? d_user : t.dU));
+                     l == 0 ? d_user : t.dU, l < cfg->n_layer - 1 ? t.hand_u : nullptr, l > 0 ? &below : nullptr));
   }
   return 0;
 }

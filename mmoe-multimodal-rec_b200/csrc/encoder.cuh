@@ -179,19 +179,33 @@ inline int enc_fwd(const EncCtx& c, const EncW& w, const float* x_prev, const vo
   return 0;
 }
 
-// dy: gradient w.r.t. the layer output (fp32 [M,d]); dx: gradient w.r.t. the layer input (fp32, may alias dy)
+// Hand-off between stacked layers: the layer ABOVE finishes with a LayerNorm backward that produces this layer's output
+// gradient; it can write the 16-bit, dropout-masked copy the FFN2 backward needs (and d b2) in the same pass.
+struct EncHandoff {
+  void* g16;            // [M,d] 16-bit: drop2-masked output gradient of the layer below
+  float* b2_grad;       // its FFN2 bias gradient (column sums of g16)
+  uint32_t site0;       // dropout site base of the layer below
+};
+
+// dy: gradient w.r.t. the layer output (fp32 [M,d]); dx: gradient w.r.t. the layer input (fp32, may alias dy).
+// dy16: if non-null, the layer above already produced cast_drop(dy) and d b2 (EncHandoff).  below: if non-null, do the same
+// for the layer below.
 inline int enc_bwd(const EncCtx& c, const EncW& w, const EncG& g, const float* x_in, const EncSaved& s, const EncScratch& t,
-                   const float* dy, float* dx) {
+                   const float* dy, float* dx, const void* dy16 = nullptr, const EncHandoff* below = nullptr) {
   const int d = c.d, ff = c.ff; const int M = (int)c.M;
   const size_t es = dtype_size(c.dtype);
   uint32_t k0, k1;
   // FFN2: x2 = x1 + drop2(h W2^T + b2)
-  site_keys(c.seed, c.site0 + 3, &k0, &k1);
-  MMOE_TRY(cast_drop_colsum(dy, t.g, g.b2, M, d, c.drop_p, k0, k1, c.dtype, c.stream));
+  const void* g2 = dy16;
+  if (g2 == nullptr) {
+    site_keys(c.seed, c.site0 + 3, &k0, &k1);
+    MMOE_TRY(cast_drop_colsum(dy, t.g, g.b2, M, d, c.drop_p, k0, k1, c.dtype, c.stream));
+    g2 = t.g;
+  }
   {
     mmoe_epilogue e = epi_none();
     e.out = t.dh; e.out_dtype = c.dtype; e.ldo = ff;
-    mmoe_gemm_problem p[2] = {linear_dgrad(t.g, d, w.w2, M, d, ff, e), linear_wgrad(t.g, d, s.h, ff, g.w2, M, d, ff)};
+    mmoe_gemm_problem p[2] = {linear_dgrad(g2, d, w.w2, M, d, ff, e), linear_wgrad(g2, d, s.h, ff, g.w2, M, d, ff)};
     MMOE_TRY(gemm_grouped(p, 2, c.dtype, 0, c.stream));
   }
   // ReLU (+dropout) backward: the kept/active pattern is h != 0; also yields d b1
@@ -241,6 +255,11 @@ inline int enc_bwd(const EncCtx& c, const EncW& w, const EncG& g, const float* x
     LnBwdArgs a{};
     a.dy = t.dxn; a.dy_dtype = c.dtype; a.x = x_in; a.x_dtype = MMOE_F32; a.stats = s.st1; a.gamma = w.ln1_w;
     a.dres = t.dx1; a.dx = dx; a.dgamma = g.ln1_w; a.dbeta = g.ln1_b;
+    if (below != nullptr) {
+      a.g_out = below->g16; a.g_colsum = below->b2_grad;
+      site_keys(c.seed, below->site0 + 3, &k0, &k1);
+      a.drop_p = c.drop_p; a.k0 = k0; a.k1 = k1;
+    }
     a.rows = M; a.d = d; a.dtype = c.dtype;
     MMOE_TRY(layernorm_bwd(a, c.stream));
   }

@@ -126,7 +126,7 @@ static FuseSaved fuse_layout(Arena& A, const mmoe_fuse_cfg& cfg, int B, int dtyp
   if (!home) { s.st_y = (float*)A.take(Bz * 2 * 4); s.yn = A.take(Bz * d * es); s.zp = A.take(Bz * d * es); }
   return s;
 }
-struct FuseScratch { EncScratch enc; float* dy; void* dzp; void* dyn; float* dX; void* dzg; float* dr; void* gr; };
+struct FuseScratch { EncScratch enc; float* dy; void* dzp; void* dyn; float* dX; void* dzg; float* dr; void* gr; void* hand; };
 static FuseScratch fuse_scratch_layout(Arena& A, const mmoe_fuse_cfg& cfg, int B, int dtype) {
   FuseScratch t{};
   const int d = cfg.d; const size_t es = dtype_size(dtype); const size_t Bz = (size_t)B;
@@ -134,6 +134,7 @@ static FuseScratch fuse_scratch_layout(Arena& A, const mmoe_fuse_cfg& cfg, int B
   t.dy = (float*)A.take(Bz * d * 4); t.dzp = A.take(Bz * d * es); t.dyn = A.take(Bz * d * es);
   t.dX = (float*)A.take(Bz * 2 * d * 4); t.dzg = A.take(Bz * (d / 2) * es);
   t.dr = (float*)A.take(Bz * d * 4); t.gr = A.take(Bz * d * es);
+  t.hand = A.take(Bz * 2 * d * es);
   return t;
 }
 static int check_fuse(const mmoe_fuse_cfg* cfg) {
@@ -255,7 +256,9 @@ static int fuse_bwd_t(const mmoe_call* c, const mmoe_fuse_cfg* cfg, const float*
   for (int l = cfg->depth - 1; l >= 0; --l) {
     ec.site0 = 16 * l;
     const float* x_in = l == 0 ? s.x0 : s.layer[l].x_sum;
-    MMOE_TRY(enc_bwd(ec, enc_w(P + ix.layer0 + 12 * l), enc_g(G + ix.layer0 + 12 * l), x_in, s.layer[l], t.enc, t.dX, t.dX));
+    EncHandoff below{t.hand, l > 0 ? enc_g(G + ix.layer0 + 12 * (l - 1)).b2 : nullptr, (uint32_t)(16 * (l - 1))};
+    MMOE_TRY(enc_bwd(ec, enc_w(P + ix.layer0 + 12 * l), enc_g(G + ix.layer0 + 12 * l), x_in, s.layer[l], t.enc, t.dX, t.dX,
+                     l < cfg->depth - 1 ? t.hand : nullptr, l > 0 ? &below : nullptr));
   }
   // identity = LN(res_proj(cat)); its gradient is dy
   {
