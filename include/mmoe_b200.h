@@ -91,7 +91,8 @@ typedef struct {
   const void* a; int64_t lda; int32_t a_major;
   const void* b; int64_t ldb; int32_t b_major;
   int32_t M, N, K;
-  int32_t k_splits;         /* >1 splits K over CTAs; requires epi.accumulate              */
+  int32_t k_splits;         /* >1 splits K over CTAs; requires epi.accumulate; 0 = let the
+                               launcher choose (1 unless epi.accumulate)                    */
   mmoe_epilogue epi;
 } mmoe_gemm_problem;
 

@@ -97,17 +97,6 @@ struct EncCtx {
   cudaStream_t stream;
 };
 
-inline int wgrad_splits(int M, int N, int K) {
-  const int tiles = ((M + 127) / 128) * ((N + 255) / 256);
-  const int kb = (K + 63) / 64;
-  int ks = (2 * sm_count() + tiles - 1) / tiles;
-  // every split adds M*N fp32 atomics (the L2 retires ~0.2 T atomics/s: a 3072x768 gradient costs ~13 us per split), so a
-  // split must carry at least 8 K-blocks of MMA work
-  const int max_ks = kb / 8 > 1 ? kb / 8 : 1;
-  if (ks > max_ks) ks = max_ks;
-  return ks < 1 ? 1 : ks;
-}
-
 // y = epilogue(x W^T + b): nn.Linear forward
 inline mmoe_gemm_problem linear_fwd(const void* x, int64_t ldx, const void* w, int M, int N, int K, const mmoe_epilogue& e) {
   return gemm_problem(x, ldx, 0, w, K, 0, M, N, K, e);
@@ -120,7 +109,7 @@ inline mmoe_gemm_problem linear_dgrad(const void* dy, int64_t lddy, const void* 
 inline mmoe_gemm_problem linear_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx, float* dw, int M, int N, int K) {
   mmoe_epilogue e = epi_none();
   e.out = dw; e.out_dtype = MMOE_F32; e.ldo = K; e.accumulate = 1;
-  return gemm_problem(dy, lddy, 1, x, ldx, 1, N, K, M, e, wgrad_splits(N, K, M));
+  return gemm_problem(dy, lddy, 1, x, ldx, 1, N, K, M, e, 0 /* split count chosen by the GEMM launcher */);
 }
 
 // x_prev (+ delta_prev, 16-bit, may be null) is the layer input.  On return the layer output is s.x1 + s.y2 (pending).

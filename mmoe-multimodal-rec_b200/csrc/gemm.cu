@@ -877,7 +877,10 @@ static int fill_epi(EpiDev* d, const mmoe_gemm_problem& pr, int dtype) {
 }
 
 extern std::atomic<int> g_sm_reserve;
-static int launch_tc(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream_t stream) {
+static int launch_tc(const mmoe_gemm_problem* pr_in, int n, int dtype, cudaStream_t stream) {
+  // k_splits == 0 on an accumulating problem means "choose": resolved below once the tile shape of the launch is known
+  mmoe_gemm_problem pr[kMaxGroups];
+  for (int i = 0; i < n; ++i) pr[i] = pr_in[i];
   TcParams P{};
   P.n_groups = n;
   P.fmt = dtype == MMOE_BF16 ? 1 : 0;
@@ -908,6 +911,22 @@ static int launch_tc(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream_t
   }
   P.bn = bn;
   const int tile_m = TBM * ctas;
+  // Tiles are dealt to the CTAs (or pairs) round-robin in list order, long split-K tiles first, so the launch is balanced
+  // when the long tiles number about one per CTA: pick the split count that makes tiles * splits ~ the CTA count, keeping
+  // at least 8 K-blocks per split (every split costs M*N fp32 atomics).  Measured at M = 32768: {dgrad FFN1 | wgrad W1}
+  // 257 / 224 / 236 / 231 / 244 us for 1..5 splits (36 pair tiles: 2 splits = 72 ~ 74 pairs).
+  for (int i = 0; i < n; ++i) {
+    if (pr[i].k_splits != 0) continue;
+    pr[i].k_splits = 1;
+    if (!pr[i].epi.accumulate || pr[i].epi.act != 0 || pr[i].epi.preact != nullptr || pr[i].epi.bwd_mode != 0) continue;
+    const int t = ((pr[i].M + tile_m - 1) / tile_m) * ((pr[i].N + bn - 1) / bn);
+    const int units = sm_count() / ctas;
+    const int kb = (pr[i].K + TBK - 1) / TBK;
+    int ks = (units + t / 2) / (t > 0 ? t : 1);
+    const int max_ks = kb / 8 > 1 ? kb / 8 : 1;
+    if (ks > max_ks) ks = max_ks;
+    pr[i].k_splits = ks < 1 ? 1 : ks;
+  }
   int tiles = 0;
   bool rich = false;
   // longest tiles first: the persistent tile list is walked in group order, and a split-K weight-gradient tile (hundreds

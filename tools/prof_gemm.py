@@ -71,8 +71,7 @@ def run_bwd_pair(name, N_out, K_in):
     w.a, w.lda, w.a_major = dY.data_ptr(), N_out, 1
     w.b, w.ldb, w.b_major = X.data_ptr(), K_in, 1
     w.M, w.N, w.K = N_out, K_in, M
-    tiles = ((N_out + 127) // 128) * ((K_in + 255) // 256)                  # encoder.cuh: wgrad_splits
-    w.k_splits = int(os.environ.get("PROF_SPLITS", "0")) or max(1, min(-(-2 * 148 // tiles), max(1, (M + 63) // 64 // 8)))
+    w.k_splits = int(os.environ.get("PROF_SPLITS", "0"))                    # 0 = chosen by the launcher
     w.epi.alpha, w.epi.out, w.epi.out_dtype, w.epi.ldo, w.epi.accumulate = 1.0, dW.data_ptr(), 0, K_in, 1
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     check(L.mmoe_gemm_grouped(P, 2, 1, 0, st), "gemm")
