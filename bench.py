@@ -216,7 +216,7 @@ def workload_config(B, n_gpus):
             "per_gpu_batch": B, "global_batch": B * n_gpus, "sentences": S, "d_model": D, "parallelism": f"dp{n_gpus}",
             "autocast": "bf16", "l2": "inputs (~0.5 GB/step) and activations (~3 GB) exceed the 126 MB L2; no flush needed",
             "encoders": "text encoders / ViT backbone excluded (reference torch modules, timed separately)",
-            "streams": "concat_ti (EnhancedCrossFuse) runs on a side stream next to the cross expert and concat_ui"}
+            "streams": "the two EnhancedCrossFuse experts run on side streams next to the cross expert"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -300,6 +300,7 @@ def main():
     grad_keys = ("u_sent", "i_sent", "u_doc", "i_doc")
 
     side_stream = None if args.no_side_stream else torch.cuda.Stream(device=dev)
+    side2 = torch.cuda.Stream(device=dev) if side_stream is not None else None
     use_side = [side_stream is not None]
     if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
         torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)     # intentional: see step()
@@ -313,13 +314,23 @@ def main():
             side = side_stream if use_side[0] else None
             if side is not None:
                 # the two fuse experts are independent, latency-bound chains of ~100 small launches each (2 tokens per
-                # sample): one of them runs on a side stream, forward and (through autograd's stream tracking) backward
+                # sample): they run on side streams, forward and (through autograd's stream tracking) backward
                 main = torch.cuda.current_stream()
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
                     xti = cti_c(ins["i_doc"], img_vec)
+                if side2 is not None:
+                    side2.wait_stream(main)
+                    with torch.cuda.stream(side2):
+                        xui = cui_c(ins["u_doc"], img_vec)
                 ui = cross_c(ins["u_sent"], ins["u_mask"], ins["i_sent"], ins["i_mask"])
-                xui = cui_c(ins["u_doc"], img_vec)
+                if side2 is None:
+                    xui = cui_c(ins["u_doc"], img_vec)
+                else:
+                    main.wait_stream(side2)
+                    xui.record_stream(main)
+                    img_vec.record_stream(side2)
+                    ins["u_doc"].record_stream(side2)
                 main.wait_stream(side)
                 xti.record_stream(main)
                 img_vec.record_stream(side)
@@ -444,7 +455,15 @@ def main():
         last = float(loss_host[n - 1])
         return last
 
-    e2e_loop(3)
+    # warm the host->device path first (the PCIe link and the pinned pages need a few hundred ms of traffic before the
+    # copy rate is steady: cold runs measured 32 K samples/s end to end, warm ones 44 K, with the same device time)
+    t_warm = time.perf_counter()
+    while time.perf_counter() - t_warm < 1.0:
+        with torch.cuda.stream(copy_stream):
+            for v in host[0].values():
+                v.to(dev, non_blocking=True)
+        copy_stream.synchronize()
+    e2e_loop(5)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0 = time.perf_counter()

@@ -22,6 +22,40 @@ struct PoolDev {
   uint32_t thresh, k0, k1; float drop_scale;
 };
 
+// 4 consecutive elements of a row as fp32 (16-byte / 8-byte accesses; d % 8 == 0 keeps them aligned)
+template <typename T> __device__ __forceinline__ float4 pool_ld4(const T* p);
+template <> __device__ __forceinline__ float4 pool_ld4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float4 pool_ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
+}
+template <> __device__ __forceinline__ float4 pool_ld4<__half>(const __half* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T> __device__ __forceinline__ void pool_st4(T* p, float4 v, float4& stored);
+template <> __device__ __forceinline__ void pool_st4<float>(float* p, float4 v, float4& stored) { *reinterpret_cast<float4*>(p) = v; stored = v; }
+template <> __device__ __forceinline__ void pool_st4<__nv_bfloat16>(__nv_bfloat16* p, float4 v, float4& stored) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u; u.x = *reinterpret_cast<const uint32_t*>(&lo); u.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+  stored = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+}
+template <> __device__ __forceinline__ void pool_st4<__half>(__half* p, float4 v, float4& stored) {
+  const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+  uint2 u; u.x = *reinterpret_cast<const uint32_t*>(&lo); u.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+  stored = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+}
+__device__ __forceinline__ float4 pool_mix(float alpha, float4 u, float4 c) {
+  const float be = 1.f - alpha;
+  return make_float4(alpha * u.x + be * c.x, alpha * u.y + be * c.y, alpha * u.z + be * c.z, alpha * u.w + be * c.w);
+}
+__device__ __forceinline__ float pool_dot(float4 a, float4 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
+
+// One CTA per sample.  Pass 1 (a warp per sentence row, 16-byte loads, the whole row in flight at once): scores of the
+// gate-mixed rows against the pooling query.  Pass 2 (a thread per 4 columns, rows from L2): the weighted sum.
 template <typename T>
 __global__ void __launch_bounds__(256) pool_fwd_kernel(const PoolDev a) {
   __shared__ float sc[64];
@@ -33,10 +67,9 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(const PoolDev a) {
   const float inv_sqrt_d = rsqrtf((float)d);
   for (int i = warp; i < S; i += 8) {
     float acc = 0.f;
-    for (int c = lane; c < d; c += 32) {
-      const float f = alpha * U[i * d + c] + (1.f - alpha) * to_f<T>(C[i * d + c]);
-      acc = fmaf(f, a.query[c], acc);
-    }
+#pragma unroll 8
+    for (int c = lane * 4; c < d; c += 128)
+      acc += pool_dot(pool_mix(alpha, pool_ld4<float>(U + i * d + c), pool_ld4<T>(C + i * d + c)), pool_ld4<float>(a.query + c));
     acc = warp_sum(acc) * inv_sqrt_d;
     if (lane == 0) sc[i] = a.mask[(int64_t)b * S + i] ? -INFINITY : acc;
   }
@@ -61,13 +94,15 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(const PoolDev a) {
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < d; c += 256) {
-    float acc = 0.f;
+  for (int c = threadIdx.x * 4; c < d; c += 1024) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
     for (int i = 0; i < S; ++i) {
-      const float f = alpha * U[i * d + c] + (1.f - alpha) * to_f<T>(C[i * d + c]);
-      acc = fmaf(sc[i], f, acc);
+      const float4 f = pool_mix(alpha, pool_ld4<float>(U + i * d + c), pool_ld4<T>(C + i * d + c));
+      const float w = sc[i];
+      acc.x = fmaf(w, f.x, acc.x); acc.y = fmaf(w, f.y, acc.y); acc.z = fmaf(w, f.z, acc.z); acc.w = fmaf(w, f.w, acc.w);
     }
-    a.pooled[(int64_t)b * d + c] = acc;
+    *reinterpret_cast<float4*>(a.pooled + (int64_t)b * d + c) = acc;
   }
 }
 
@@ -86,10 +121,9 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const PoolDev a) {
   // dwd[i] = <dpooled, fused_i>
   for (int i = warp; i < S; i += 8) {
     float acc = 0.f;
-    for (int c = lane; c < d; c += 32) {
-      const float f = alpha * U[i * d + c] + (1.f - alpha) * to_f<T>(C[i * d + c]);
-      acc = fmaf(f, dp[c], acc);
-    }
+#pragma unroll 8
+    for (int c = lane * 4; c < d; c += 128)
+      acc += pool_dot(pool_mix(alpha, pool_ld4<float>(U + i * d + c), pool_ld4<T>(C + i * d + c)), pool_ld4<float>(dp + c));
     acc = warp_sum(acc);
     if (lane == 0) ds[i] = acc;
   }
@@ -119,22 +153,25 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const PoolDev a) {
   float dalpha = 0.f;
   float* dU = a.dU + (int64_t)b * S * d;
   T* dC = (T*)a.dC + (int64_t)b * S * d;
-  for (int c = threadIdx.x; c < d; c += 256) {
-    const float q = a.query[c], dpc = dp[c];
-    float dq = 0.f, dbo = 0.f;
+  const float be = 1.f - alpha;
+  for (int c = threadIdx.x * 4; c < d; c += 1024) {
+    const float4 q = pool_ld4<float>(a.query + c), dpc = pool_ld4<float>(dp + c);
+    float4 dq = make_float4(0.f, 0.f, 0.f, 0.f), dbo = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
     for (int i = 0; i < S; ++i) {
-      const float u = U[i * d + c], cc = to_f<T>(C[i * d + c]);
-      const float f = alpha * u + (1.f - alpha) * cc;
-      const float df = wd[i] * dpc + ds[i] * q;
-      dq = fmaf(ds[i], f, dq);
-      dalpha = fmaf(df, u - cc, dalpha);
-      dU[i * d + c] = alpha * df;
-      const T o = from_f<T>((1.f - alpha) * df);
-      dC[i * d + c] = o;
-      dbo += to_f<T>(o);
+      const float4 u = pool_ld4<float>(U + i * d + c), cc = pool_ld4<T>(C + i * d + c);
+      const float4 f = pool_mix(alpha, u, cc);
+      const float w = wd[i], s_ = ds[i];
+      const float4 df = make_float4(fmaf(w, dpc.x, s_ * q.x), fmaf(w, dpc.y, s_ * q.y), fmaf(w, dpc.z, s_ * q.z), fmaf(w, dpc.w, s_ * q.w));
+      dq.x = fmaf(s_, f.x, dq.x); dq.y = fmaf(s_, f.y, dq.y); dq.z = fmaf(s_, f.z, dq.z); dq.w = fmaf(s_, f.w, dq.w);
+      dalpha += df.x * (u.x - cc.x) + df.y * (u.y - cc.y) + df.z * (u.z - cc.z) + df.w * (u.w - cc.w);
+      *reinterpret_cast<float4*>(dU + i * d + c) = make_float4(alpha * df.x, alpha * df.y, alpha * df.z, alpha * df.w);
+      float4 o;
+      pool_st4<T>(dC + i * d + c, make_float4(be * df.x, be * df.y, be * df.z, be * df.w), o);
+      dbo.x += o.x; dbo.y += o.y; dbo.z += o.z; dbo.w += o.w;
     }
-    atomicAdd(a.dquery + c, dq);
-    atomicAdd(a.dbo + c, dbo);
+    atomicAdd(a.dquery + c + 0, dq.x); atomicAdd(a.dquery + c + 1, dq.y); atomicAdd(a.dquery + c + 2, dq.z); atomicAdd(a.dquery + c + 3, dq.w);
+    atomicAdd(a.dbo + c + 0, dbo.x); atomicAdd(a.dbo + c + 1, dbo.y); atomicAdd(a.dbo + c + 2, dbo.z); atomicAdd(a.dbo + c + 3, dbo.w);
   }
   dalpha = warp_sum(dalpha);
   if (lane == 0) red[warp] = dalpha;
