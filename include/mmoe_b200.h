@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define MMOE_ABI_VERSION 1
+#define MMOE_ABI_VERSION 2
 
 typedef enum { MMOE_F32 = 0, MMOE_BF16 = 1, MMOE_F16 = 2 } mmoe_dtype;
 
@@ -76,8 +76,10 @@ typedef struct {
   int32_t      act;         /* 0 none, 1 ReLU, 2 GELU(erf), 3 sigmoid                       */
   int32_t      bwd_mode;    /* 0 none; 1: v *= (aux != 0) (ReLU[+dropout] backward, aux =    */
                             /*    saved post-dropout output; scale by 1/(1-p) if drop_p>0);  */
-                            /* 2: v *= gelu'(aux); 3: v *= s(1-s), s = sigmoid(aux)          */
-  const void*  aux;         /* T [M, ld_aux]                                                */
+                            /* 2: v *= gelu'(aux); 3: v *= s(1-s), s = sigmoid(aux);         */
+                            /* 4: as 1, but aux is the BIT mask written through mask_out     */
+                            /*    (uint64 [M, N/64]); 16-bit tensor-core path only           */
+  const void*  aux;         /* T [M, ld_aux]  (mode 4: uint64 [M, N/64], ld_aux ignored)    */
   int64_t      ld_aux;
   const float* residual;    /* fp32 [M, ld_res] or NULL, added last                         */
   int64_t      ld_res;
@@ -85,6 +87,9 @@ typedef struct {
   float        alpha;
   float        drop_p;      /* dropout after the activation / backward multiplier           */
   uint32_t     drop_key0, drop_key1;   /* mask(m,n) = f(key, m*N + n), see mmoe_dropout_mask */
+  void*        mask_out;    /* uint64 [M, N/64] or NULL: bit n%64 of word [m, n/64] = (stored value != 0).
+                               Lets the ReLU(+dropout) backward read 1 bit per element instead of the saved
+                               activation.  16-bit tensor-core path only (N % 64 == 0); fails loudly otherwise. */
 } mmoe_epilogue;
 
 typedef struct {

@@ -23,7 +23,7 @@ class Epilogue(C.Structure):
         ("bias", C.c_void_p), ("preact", C.c_void_p), ("act", C.c_int32), ("bwd_mode", C.c_int32),
         ("aux", C.c_void_p), ("ld_aux", C.c_int64), ("residual", C.c_void_p), ("ld_res", C.c_int64),
         ("colsum", C.c_void_p), ("alpha", C.c_float), ("drop_p", C.c_float),
-        ("drop_key0", C.c_uint32), ("drop_key1", C.c_uint32),
+        ("drop_key0", C.c_uint32), ("drop_key1", C.c_uint32), ("mask_out", C.c_void_p),
     ]
 
 

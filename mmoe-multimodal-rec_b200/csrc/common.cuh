@@ -161,6 +161,7 @@ inline int sm_count() {
 
 // ---------------------------------------------------------------- GEMM engine entry (gemm.cu)
 int gemm_grouped(const mmoe_gemm_problem* problems, int n_problems, int dtype, int engine, cudaStream_t stream);
+bool gemm_bitmask_supported(int dtype, int64_t M, int N);
 
 // convenience builders used by the orchestrators
 inline mmoe_epilogue epi_none() {

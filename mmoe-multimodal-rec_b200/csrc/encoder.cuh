@@ -58,6 +58,7 @@ inline EncG enc_g(void* const* p) {
 struct EncSaved {
   float* x_sum;   // layer input when it arrived as (x_prev + delta_prev); unused for a layer fed directly
   void* xn1; float* st1; void* qkv; void* ctx; void* y1; float* x1; void* xn2; float* st2; void* h; void* y2;
+  uint64_t* hbits;   // [M, ff/64]: bit = (h != 0), the ReLU/dropout pattern of the FFN hidden layer (16-bit modes)
 };
 inline EncSaved enc_layout(Arena& A, int64_t M, int d, int ff, size_t es) {
   EncSaved s;
@@ -72,6 +73,7 @@ inline EncSaved enc_layout(Arena& A, int64_t M, int d, int ff, size_t es) {
   s.st2 = (float*)A.take(M * 2 * sizeof(float));
   s.h = A.take(M * ff * es);
   s.y2 = A.take(M * d * es);
+  s.hbits = (uint64_t*)A.take(M * ((ff + 63) / 64) * sizeof(uint64_t));
   return s;
 }
 // scratch of the backward pass
@@ -152,6 +154,7 @@ inline int enc_fwd(const EncCtx& c, const EncW& w, const float* x_prev, const vo
   {
     mmoe_epilogue e = epi_none();
     e.out = s.h; e.out_dtype = c.dtype; e.ldo = ff; e.bias = w.b1; e.act = 1;
+    if (gemm_bitmask_supported(c.dtype, M, ff)) e.mask_out = s.hbits;      // 1 bit per element for the backward
     site_keys(c.seed, c.site0 + 2, &k0, &k1);
     e.drop_p = c.drop_p; e.drop_key0 = k0; e.drop_key1 = k1;
     mmoe_gemm_problem p = linear_fwd(s.xn2, d, w.w1, M, ff, d, e);
@@ -191,14 +194,18 @@ inline int enc_bwd(const EncCtx& c, const EncW& w, const EncG& g, const float* x
     MMOE_TRY(cast_drop_colsum(dy, t.g, g.b2, M, d, c.drop_p, k0, k1, c.dtype, c.stream));
     g2 = t.g;
   }
+  const bool bits = gemm_bitmask_supported(c.dtype, M, ff);
   {
+    // ReLU (+dropout) backward: the kept/active pattern is h != 0.  16-bit modes: the dgrad epilogue applies the bit
+    // pattern the forward FFN1 epilogue wrote and sums d b1 (K = 3072 leaves that epilogue plenty of slack).
     mmoe_epilogue e = epi_none();
     e.out = t.dh; e.out_dtype = c.dtype; e.ldo = ff;
+    if (bits) { e.bwd_mode = 4; e.aux = s.hbits; e.drop_p = c.drop_p; e.colsum = g.b1; }
     mmoe_gemm_problem p[2] = {linear_dgrad(g2, d, w.w2, M, d, ff, e), linear_wgrad(g2, d, s.h, ff, g.w2, M, d, ff)};
     MMOE_TRY(gemm_grouped(p, 2, c.dtype, 0, c.stream));
   }
-  // ReLU (+dropout) backward: the kept/active pattern is h != 0; also yields d b1
-  MMOE_TRY(relu_mask_colsum(t.dh, s.h, g.b1, M, ff, c.drop_p > 0.f ? 1.f / (1.f - c.drop_p) : 1.f, c.dtype, c.stream));
+  if (!bits)
+    MMOE_TRY(relu_mask_colsum(t.dh, s.h, g.b1, M, ff, c.drop_p > 0.f ? 1.f / (1.f - c.drop_p) : 1.f, c.dtype, c.stream));
   // FFN1: h = drop(relu(xn2 W1^T + b1))
   {
     mmoe_epilogue e = epi_none();

@@ -389,10 +389,12 @@ __device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int tile) {
 //   SCALED: the bias table already holds bias * dscale and the dropout scale is folded into one FFMA (act <= 1 only)
 //   DROP  : keyed-hash dropout; the pair index fits 32 bits (checked on the host), so the high-word term of drop_hash
 //           vanishes and the key mix is hoisted; keep tests are done on the raw 32-bit hash (no field extraction)
-template <int ACT, bool DROP, bool SCALED, bool BF16>
-__device__ __forceinline__ void epi_chunk_math(const uint32_t (&v)[64], const float* tab, uint32_t (&pk)[32], float dscale,
-                                               uint32_t thresh, uint32_t dk0, uint32_t dk1, uint32_t pair0) {
+//   MASK  : also returns bit j = (value j != 0) for the 64 values (the ReLU / dropout pattern, for mask_out)
+template <int ACT, bool DROP, bool SCALED, bool BF16, bool MASK = false>
+__device__ __forceinline__ uint64_t epi_chunk_math(const uint32_t (&v)[64], const float* tab, uint32_t (&pk)[32], float dscale,
+                                                   uint32_t thresh, uint32_t dk0, uint32_t dk1, uint32_t pair0) {
   const uint32_t thi = thresh << 16;
+  uint32_t bits_lo = 0u, bits_hi = 0u;
 #pragma unroll
   for (int j = 0; j < 64; j += 2) {
     const float2 bb = *reinterpret_cast<const float2*>(tab + j);           // warp-uniform address: smem broadcast
@@ -412,14 +414,25 @@ __device__ __forceinline__ void epi_chunk_math(const uint32_t (&v)[64], const fl
       else { v0 = k0 ? v0 * dscale : 0.f; v1 = k1 ? v1 * dscale : 0.f; }
     }
     pk[j >> 1] = BF16 ? pack_bf16(v0, v1) : pack_f16(v0, v1);
+    if (MASK) {
+      const uint32_t b2 = (v0 != 0.f ? 1u : 0u) | (v1 != 0.f ? 2u : 0u);
+      if (j < 32) bits_lo |= b2 << (j & 31); else bits_hi |= b2 << (j & 31);
+    }
   }
+  return ((uint64_t)bits_hi << 32) | bits_lo;
 }
 template <bool RICH, bool BF16>
-__device__ __forceinline__ void epi_chunk_dispatch(int act, bool drop, bool scaled, const uint32_t (&v)[64], const float* tab,
-                                                   uint32_t (&pk)[32], float dscale, uint32_t thresh, uint32_t dk0, uint32_t dk1,
-                                                   uint32_t pair0) {
+__device__ __forceinline__ uint64_t epi_chunk_dispatch(int act, bool drop, bool scaled, bool want_mask, const uint32_t (&v)[64],
+                                                       const float* tab, uint32_t (&pk)[32], float dscale, uint32_t thresh,
+                                                       uint32_t dk0, uint32_t dk1, uint32_t pair0) {
+  if (RICH && want_mask) {             // ReLU (+dropout) with the bit mask (host checks act == 1)
+    if (!drop) return epi_chunk_math<1, false, false, BF16, true>(v, tab, pk, dscale, thresh, dk0, dk1, pair0);
+    if (scaled) return epi_chunk_math<1, true, true, BF16, true>(v, tab, pk, dscale, thresh, dk0, dk1, pair0);
+    return epi_chunk_math<1, true, false, BF16, true>(v, tab, pk, dscale, thresh, dk0, dk1, pair0);
+  }
   if (act == 0) {
-    if (!drop) epi_chunk_math<0, false, false, BF16>(v, tab, pk, dscale, thresh, dk0, dk1, pair0);
+    if (!drop && scaled) epi_chunk_math<0, false, true, BF16>(v, tab, pk, dscale, thresh, dk0, dk1, pair0);   // bit-mask backward
+    else if (!drop) epi_chunk_math<0, false, false, BF16>(v, tab, pk, dscale, thresh, dk0, dk1, pair0);
     else if (scaled) epi_chunk_math<0, true, true, BF16>(v, tab, pk, dscale, thresh, dk0, dk1, pair0);
     else epi_chunk_math<0, true, false, BF16>(v, tab, pk, dscale, thresh, dk0, dk1, pair0);
   } else if (act == 1) {
@@ -433,6 +446,7 @@ __device__ __forceinline__ void epi_chunk_dispatch(int act, bool drop, bool scal
     if (!drop) epi_chunk_math<3, false, false, BF16>(v, tab, pk, dscale, thresh, dk0, dk1, pair0);
     else epi_chunk_math<3, true, false, BF16>(v, tab, pk, dscale, thresh, dk0, dk1, pair0);
   }
+  return 0ull;
 }
 
 // BN: tile width (compile-time so the TMA issue loop and the instruction descriptor are constants — the pipeline is
@@ -627,8 +641,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         // can be folded into the accumulator FFMA)
         float* tab = bias_tab + ew * 64;
         const bool has_pre = RICH && preact != nullptr;
-        const bool drop = thresh != 0u;
-        const bool scaled = drop && act <= 1 && !has_pre;
+        const bool bitmode = RICH && bwd_mode == 4;            // dY . W^T masked by the saved ReLU/dropout bit pattern
+        const bool drop = thresh != 0u && !bitmode;
+        const bool scaled = (drop && act <= 1 && !has_pre) || (bitmode && e.drop_p > 0.0f);
+        uint64_t* const mask_out = RICH ? reinterpret_cast<uint64_t*>(e.mask_out) : nullptr;
+        const int words = N >> 6;                              // 64-column mask words per row
         bool released = false;
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
@@ -647,6 +664,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * TBN + col0);
           tmem_ld32_nowait(taddr, v);
           tmem_ld32_nowait(taddr + 32, v + 32);
+          uint64_t inbits = 0ull;
+          if (bitmode && m < g.M) inbits = __ldg(reinterpret_cast<const uint64_t*>(aux) + m * words + (nb >> 6));
           __syncwarp();                          // every lane is done reading the previous chunk's table
           *reinterpret_cast<float2*>(tab + lane * 2) = bv;
           tmem_ld_wait();
@@ -684,8 +703,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
             }
             store_pending = true;
           }
-          if (is_bf16) epi_chunk_dispatch<RICH, true>(act, drop, scaled, v, tab, pk, dscale, thresh, dk0, dk1, pair0);
-          else epi_chunk_dispatch<RICH, false>(act, drop, scaled, v, tab, pk, dscale, thresh, dk0, dk1, pair0);
+          uint64_t outbits;
+          if (is_bf16) outbits = epi_chunk_dispatch<RICH, true>(act, drop, scaled, mask_out != nullptr, v, tab, pk, dscale, thresh, dk0, dk1, pair0);
+          else outbits = epi_chunk_dispatch<RICH, false>(act, drop, scaled, mask_out != nullptr, v, tab, pk, dscale, thresh, dk0, dk1, pair0);
+          if (RICH && mask_out != nullptr && m < g.M) mask_out[m * words + (nb >> 6)] = outbits;
+          if (bitmode) {
+            // keep the 16-bit halves whose bit is set (rows >= M carry inbits = 0 and contribute nothing to the column sums)
+#pragma unroll
+            for (int w = 0; w < 32; ++w) {
+              const uint32_t b2 = (uint32_t)(inbits >> (2 * w)) & 3u;
+              pk[w] &= ((b2 & 1u) * 0xFFFFu) | ((b2 >> 1) * 0xFFFF0000u);
+            }
+          }
           if (store_pending) {                   // the previous TMA store must have finished reading the slab
             if (lane == 0) tma_store_wait_read();
             __syncwarp();
@@ -703,6 +732,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
             tma_store_commit();
           }
           store_pending = true;
+          if (bitmode && colsum != nullptr) {
+            // bias gradient: column sums of the (rounded, masked) tile.  Lane l re-reads 32-bit word l (columns 2l, 2l+1)
+            // of every slab row — bank (chunk ^ row) * 4 + word is a bijection over the lanes: no conflicts
+            float cs0 = 0.f, cs1 = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              uint32_t w;
+              const uint32_t src = st_addr + (uint32_t)r * 128u + (uint32_t)((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2));
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(src) : "memory");
+              if (is_bf16) { cs0 += __uint_as_float(w << 16); cs1 += __uint_as_float(w & 0xFFFF0000u); }
+              else { const __half2 hh = *reinterpret_cast<const __half2*>(&w); cs0 += __low2float(hh); cs1 += __high2float(hh); }
+            }
+            const int n = nb + 2 * lane;
+            if (n < N) { atomicAdd(colsum + n, cs0); atomicAdd(colsum + n + 1, cs1); }
+          }
         }
         if (!released) {                         // this warp's column half lies outside the matrix
           tc_fence_before();
@@ -952,8 +996,14 @@ static int launch_tc(const mmoe_gemm_problem* pr_in, int n, int dtype, cudaStrea
     MMOE_TRY(fill_epi(&g.epi, q, dtype));
     {
       const mmoe_epilogue& e = q.epi;
-      const bool fast = e.out != nullptr && e.out_dtype != MMOE_F32 && !e.accumulate && e.bwd_mode == 0 &&
-                        e.residual == nullptr && e.colsum == nullptr && e.act >= 0 && e.act <= 3 && e.alpha == 1.0f &&
+      const bool bits_ok = (q.N % 64) == 0;
+      const bool bwd_ok = e.bwd_mode == 0 ? e.colsum == nullptr
+                                          : (e.bwd_mode == 4 && bits_ok && e.aux != nullptr && e.act == 0 && e.bias == nullptr &&
+                                             e.preact == nullptr && (reinterpret_cast<uintptr_t>(e.aux) & 7) == 0);
+      const bool mask_ok = e.mask_out == nullptr || (bits_ok && e.act == 1 && e.preact == nullptr &&
+                                                     (reinterpret_cast<uintptr_t>(e.mask_out) & 7) == 0);
+      const bool fast = e.out != nullptr && e.out_dtype != MMOE_F32 && !e.accumulate && bwd_ok && mask_ok &&
+                        e.residual == nullptr && e.act >= 0 && e.act <= 3 && e.alpha == 1.0f &&
                         (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 && (e.ldo % 8) == 0 && q.k_splits <= 1 &&
                         (e.preact == nullptr || (reinterpret_cast<uintptr_t>(e.preact) & 15) == 0) &&
                         (e.drop_p <= 0.f || (uint64_t)q.M * (uint64_t)q.N <= (1ull << 33)) &&
@@ -961,7 +1011,9 @@ static int launch_tc(const mmoe_gemm_problem* pr_in, int n, int dtype, cudaStrea
       g.kind = fast ? 1 : 0;
       if (fast) MMOE_TRY(make_tmap(&g.tma_out, e.out, dtype, q.M, q.N, e.ldo, 32));
       if (fast && e.preact != nullptr) MMOE_TRY(make_tmap(&g.tma_pre, e.preact, dtype, q.M, q.N, e.ldo, 32));
-      if (fast && (e.preact != nullptr || e.act >= 2)) rich = true;
+      if (fast && (e.preact != nullptr || e.act >= 2 || e.bwd_mode == 4 || e.mask_out != nullptr)) rich = true;
+      MMOE_CHECK(fast || (e.bwd_mode != 4 && e.mask_out == nullptr),
+                 "bit-mask epilogues (bwd_mode 4 / mask_out) need the 16-bit tensor-core fast path (N %% 64 == 0, 16-byte aligned 16-bit output)");
     }
     g.tiles_m = (q.M + tile_m - 1) / tile_m;
     g.tiles_n = (q.N + bn - 1) / bn;
@@ -1017,6 +1069,8 @@ static int launch_tc(const mmoe_gemm_problem* pr_in, int n, int dtype, cudaStrea
 
 template <typename T>
 static int launch_simt(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream_t stream) {
+  for (int i = 0; i < n; ++i)
+    MMOE_CHECK(pr[i].epi.bwd_mode != 4 && pr[i].epi.mask_out == nullptr, "bit-mask epilogues are tensor-core (16-bit) only");
   SimtParams P{};
   P.n_groups = n;
   int tiles = 0;
@@ -1110,6 +1164,14 @@ static int gemm_grouped_untimed(const mmoe_gemm_problem* problems, int n_problem
     return launch_simt<__half>(problems, n_problems, dtype, stream);
   }
   return launch_tc(problems, n_problems, dtype, stream);
+}
+
+// Whether a [M, N] 16-bit output can use the bit-mask epilogues (mask_out / bwd_mode 4): callers ask before they plan a
+// forward/backward pair around them.
+bool gemm_bitmask_supported(int dtype, int64_t M, int N) {
+  static const bool debug_off = getenv("MMOE_DEBUG_FORCE_SIMT") != nullptr || getenv("MMOE_DEBUG_GENERAL_EPILOGUE") != nullptr ||
+                                getenv("MMOE_DEBUG_NO_BITMASK") != nullptr;
+  return !debug_off && dtype != MMOE_F32 && N % 64 == 0 && (uint64_t)M * (uint64_t)N <= (1ull << 33);
 }
 
 }  // namespace mmoe

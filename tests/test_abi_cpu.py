@@ -30,7 +30,7 @@ def test_struct_mirrors_match_compiled_sizes():
     import mmoe_multimodal_rec_b200 as pkg
     from mmoe_multimodal_rec_b200 import _lib
     L = pkg.lib()
-    assert L.mmoe_abi_version() == 1
+    assert L.mmoe_abi_version() == 2
     for i, st in enumerate(_lib.ABI_STRUCTS):
         assert L.mmoe_abi_sizeof(i) == C.sizeof(st), st.__name__
 

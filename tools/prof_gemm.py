@@ -36,6 +36,12 @@ def run(name, N, K, variant):
         out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
         e.out, e.out_dtype, e.ldo, e.act = out.data_ptr(), 1, N, 1
         e.drop_p, e.drop_key0, e.drop_key1 = 0.1, 123, 456
+    elif variant == "relu_drop_mask":
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        bits = torch.empty(M, N // 64, device=dev, dtype=torch.int64)
+        e.out, e.out_dtype, e.ldo, e.act, e.mask_out = out.data_ptr(), 1, N, 1, bits.data_ptr()
+        e.drop_p, e.drop_key0, e.drop_key1 = 0.1, 123, 456
+        keep.append(bits)
     elif variant == "resid_drop":
         out = torch.empty(M, N, device=dev)
         res = torch.randn(M, N, device=dev)
@@ -88,6 +94,7 @@ def run_bwd_pair(name, N_out, K_in):
 run("qkv", 2304, 768, "plain")
 run("out_proj", 768, 768, "plain")
 run("ffn1", 3072, 768, "relu_drop")
+run("ffn1+bits", 3072, 768, "relu_drop_mask")
 run("plain_k3072", 768, 3072, "plain")
 run_bwd_pair("ffn2_bwd", 768, 3072)
 run_bwd_pair("ffn1_bwd", 3072, 768)
