@@ -1085,6 +1085,13 @@ static int launch_simt(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream
     g.tiles_m = (q.M + SBM - 1) / SBM;
     g.tiles_n = (q.N + SBN - 1) / SBN;
     int ks = q.k_splits < 1 ? 1 : q.k_splits;
+    if (q.k_splits == 0 && q.epi.accumulate && q.epi.act == 0 && q.epi.preact == nullptr && q.epi.bwd_mode == 0) {
+      // "choose": about four CTAs per SM in total, at least 256 of K per split
+      const int t = g.tiles_m * g.tiles_n;
+      ks = (4 * sm_count() + t - 1) / (t > 0 ? t : 1);
+      const int max_ks = q.K / 256 > 1 ? q.K / 256 : 1;
+      if (ks > max_ks) ks = max_ks;
+    }
     int kper = ((q.K + ks - 1) / ks + SBK - 1) / SBK * SBK;
     if (kper < SBK) kper = SBK;
     g.k_per_split = kper;

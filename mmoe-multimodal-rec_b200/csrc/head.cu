@@ -684,7 +684,7 @@ static int head_bwd_t(const mmoe_call* c, const mmoe_head_cfg* cfg, const float*
   uint32_t k0, k1;
   for (int k = 0; k < 2; ++k) {
     site_keys(c->seed, 20 + k, &k0, &k1);
-    gemv_bwd_kernel<T><<<rows_grid(B, 8), 256, 0, st>>>(dlogits + (size_t)k * B, (const T*)s.a2 + (size_t)k * B * h2,
+    gemv_bwd_kernel<T><<<rows_grid(B, 4), 256, 0, st>>>(dlogits + (size_t)k * B, (const T*)s.a2 + (size_t)k * B * h2,
                                                         (const T*)s.z2 + (size_t)k * B * h2, (const float*)P[ix.w3[k]],
                                                         (T*)t.dz2 + (size_t)k * B * h2, (float*)G[ix.w3[k]], (float*)G[ix.b3[k]],
                                                         (float*)G[ix.b2[k]], B, h2, thresh, scale, k0, k1);

@@ -196,55 +196,74 @@ static __global__ void __launch_bounds__(256) mix_bwd_kernel(const MixDev a, int
 }
 
 // ---------------------------------------------------------------- dW[k][c] += sum_b coef[b][k] * X[b][c]; db[k] += sum_b coef[b][k]
-// (gate weight gradients: k <= 8 outputs).  grid = (ceil(d/64), row chunks), 256 threads.
-static __global__ void __launch_bounds__(256) small_wgrad_kernel(const float* __restrict__ coef, const void* __restrict__ X, int x_dtype,
+// (gate weight gradients: k <= 8 outputs).  A block owns a chunk of rows and ALL columns: its coefficients are staged in
+// shared memory once, a thread owns 4 adjacent columns (8- or 16-byte row loads, 8 rows in flight) and keeps the k x 4
+// partial sums in registers; one atomic per (k, column) per block at the end.
+constexpr int SWG_ROWS = 128;          // rows of coefficients staged per trip
+template <typename XT>
+static __global__ void __launch_bounds__(256) small_wgrad_kernel(const float* __restrict__ coef, const XT* __restrict__ X,
                                                           float* __restrict__ dW, float* __restrict__ db, int64_t B, int d, int n,
                                                           int64_t rows_per_block) {
-  __shared__ float red[4][MIX_MAXN][64];
-  const int cl = threadIdx.x & 63, sub = threadIdx.x >> 6;
-  const int c = blockIdx.x * 64 + cl;
-  const int64_t b0 = (int64_t)blockIdx.y * rows_per_block, b1 = min(B, b0 + rows_per_block);
-  float acc[MIX_MAXN], accb[MIX_MAXN];
+  __shared__ float cs[SWG_ROWS][MIX_MAXN];
+  const int64_t b0 = (int64_t)blockIdx.x * rows_per_block, b1 = min(B, b0 + rows_per_block);
+  const int c = threadIdx.x * 4;
+  const bool col_ok = c < d;
+  float4 acc[MIX_MAXN];
+  float accb = 0.f;                    // thread k < n sums coefficient column k
 #pragma unroll
-  for (int k = 0; k < MIX_MAXN; ++k) acc[k] = accb[k] = 0.f;
-  // 4 rows per thread per trip: all of their loads are issued before the first FMA (the loop is latency-bound otherwise)
-  for (int64_t bb = b0 + sub; bb < b1; bb += 16) {
-    float x[4], cf[4][MIX_MAXN];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int64_t b = bb + 4 * u;
-      const bool ok = b < b1;
-      x[u] = (ok && c < d) ? load_as_f(X, b * d + c, x_dtype) : 0.f;
-#pragma unroll
-      for (int k = 0; k < MIX_MAXN; ++k) cf[u][k] = (ok && k < n) ? __ldg(coef + b * n + k) : 0.f;
+  for (int k = 0; k < MIX_MAXN; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t r0 = b0; r0 < b1; r0 += SWG_ROWS) {
+    const int rows = (int)min((int64_t)SWG_ROWS, b1 - r0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < rows * MIX_MAXN; e += 256) {
+      const int r = e / MIX_MAXN, k = e - r * MIX_MAXN;
+      cs[r][k] = k < n ? coef[(r0 + r) * n + k] : 0.f;
     }
+    __syncthreads();
+    if (threadIdx.x < n)
+      for (int r = 0; r < rows; ++r) accb += cs[r][threadIdx.x];
+    if (col_ok) {
+#pragma unroll 8
+      for (int r = 0; r < rows; ++r) {
+        float4 x;
+        if (sizeof(XT) == 4) {
+          x = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(X) + (r0 + r) * d + c);
+        } else {
+          const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(X) + (r0 + r) * d + c);
+          x = make_float4(to_f<XT>(reinterpret_cast<const XT*>(&u.x)[0]), to_f<XT>(reinterpret_cast<const XT*>(&u.x)[1]),
+                          to_f<XT>(reinterpret_cast<const XT*>(&u.y)[0]), to_f<XT>(reinterpret_cast<const XT*>(&u.y)[1]));
+        }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-      for (int k = 0; k < MIX_MAXN; ++k) { acc[k] = fmaf(cf[u][k], x[u], acc[k]); accb[k] += cf[u][k]; }
+        for (int k = 0; k < MIX_MAXN; ++k) {
+          const float cf = cs[r][k];
+          acc[k].x = fmaf(cf, x.x, acc[k].x); acc[k].y = fmaf(cf, x.y, acc[k].y);
+          acc[k].z = fmaf(cf, x.z, acc[k].z); acc[k].w = fmaf(cf, x.w, acc[k].w);
+        }
+      }
+    }
   }
-#pragma unroll
-  for (int k = 0; k < MIX_MAXN; ++k) red[sub][k][cl] = acc[k];
-  __syncthreads();
-  if (sub == 0 && c < d) {
+  if (col_ok) {
 #pragma unroll
     for (int k = 0; k < MIX_MAXN; ++k)
-      if (k < n) atomicAdd(dW + k * d + c, red[0][k][cl] + red[1][k][cl] + red[2][k][cl] + red[3][k][cl]);
+      if (k < n) {
+        atomicAdd(dW + k * d + c + 0, acc[k].x); atomicAdd(dW + k * d + c + 1, acc[k].y);
+        atomicAdd(dW + k * d + c + 2, acc[k].z); atomicAdd(dW + k * d + c + 3, acc[k].w);
+      }
   }
-  if (blockIdx.x == 0 && cl == 0) {
-#pragma unroll
-    for (int k = 0; k < MIX_MAXN; ++k)
-      if (k < n) atomicAdd(db + k, accb[k]);
-  }
+  if (threadIdx.x < n) atomicAdd(db + threadIdx.x, accb);
 }
 
 inline int small_wgrad(const float* coef, const void* X, int x_dtype, float* dW, float* db, int64_t B, int d, int n, cudaStream_t s) {
-  int64_t chunks = (B + 255) / 256;
-  if (chunks > 128) chunks = 128;
-  if (chunks < 1) chunks = 1;
-  const int64_t rpb = (B + chunks - 1) / chunks;
-  dim3 grid((d + 63) / 64, (unsigned)chunks);
-  small_wgrad_kernel<<<grid, 256, 0, s>>>(coef, X, x_dtype, dW, db, B, d, n, rpb);
+  MMOE_CHECK(d % 4 == 0 && d <= 1024 && n <= MIX_MAXN, "small_wgrad: unsupported d=%d n=%d", d, n);
+  int64_t blocks = (B + 63) / 64;                       // at least 64 rows per block
+  const int64_t cap = (int64_t)sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  const int64_t rpb = (B + blocks - 1) / blocks;
+  blocks = (B + rpb - 1) / rpb;
+  if (x_dtype == MMOE_F32) small_wgrad_kernel<float><<<(int)blocks, 256, 0, s>>>(coef, (const float*)X, dW, db, B, d, n, rpb);
+  else if (x_dtype == MMOE_BF16) small_wgrad_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, s>>>(coef, (const __nv_bfloat16*)X, dW, db, B, d, n, rpb);
+  else small_wgrad_kernel<__half><<<(int)blocks, 256, 0, s>>>(coef, (const __half*)X, dW, db, B, d, n, rpb);
   MMOE_LAUNCH_OK("small_wgrad_kernel");
   return 0;
 }
@@ -265,38 +284,92 @@ __global__ void __launch_bounds__(256) gemv_fwd_kernel(const T* __restrict__ a, 
 }
 // backward through  logit = <drop(gelu(z)), w> + bias :
 //   dz[b,j] = T(dlogit[b] * w[j] * dropmask * gelu'(z[b,j]));  db_prev[j] += colsum(dz);  dw[j] += dlogit[b]*a[b,j];  dbias += dlogit
+// A lane owns 4 adjacent columns (8-byte row accesses; k % 4 == 0, k <= 512); the per-column partial sums are reduced
+// across the block's warps in shared memory, so a block issues ONE atomic per column (a warp-level atomic per column cost
+// ~100 us of same-address contention at B = 65536).
+template <typename T> __device__ __forceinline__ float4 gv_ld4(const T* p);
+template <> __device__ __forceinline__ float4 gv_ld4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float4 gv_ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
+}
+template <> __device__ __forceinline__ float4 gv_ld4<__half>(const __half* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T> __device__ __forceinline__ float4 gv_st4(T* p, float4 v);      // returns what was stored
+template <> __device__ __forceinline__ float4 gv_st4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; return v; }
+template <> __device__ __forceinline__ float4 gv_st4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u; u.x = *reinterpret_cast<const uint32_t*>(&lo); u.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+  return make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+}
+template <> __device__ __forceinline__ float4 gv_st4<__half>(__half* p, float4 v) {
+  const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+  uint2 u; u.x = *reinterpret_cast<const uint32_t*>(&lo); u.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+  return make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+}
 template <typename T>
 __global__ void __launch_bounds__(256) gemv_bwd_kernel(const float* __restrict__ dlogit, const T* __restrict__ a, const T* __restrict__ z,
                                                        const float* __restrict__ w, T* __restrict__ dz, float* __restrict__ dw,
                                                        float* __restrict__ dbias, float* __restrict__ db_prev, int64_t B, int k,
                                                        uint32_t thresh, float scale, uint32_t k0, uint32_t k1) {
-  constexpr int MAXJ = 16;   // k <= 512
-  const int lane = threadIdx.x & 31;
+  constexpr int MAXI = 4;    // k <= 512
+  __shared__ float red[8][2][512];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  float acc_w[MAXJ], acc_b[MAXJ];
+  float4 acc_w[MAXI], acc_b[MAXI], wv[MAXI];
 #pragma unroll
-  for (int i = 0; i < MAXJ; ++i) acc_w[i] = acc_b[i] = 0.f;
+  for (int i = 0; i < MAXI; ++i) {
+    acc_w[i] = acc_b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c = lane * 4 + 128 * i;
+    wv[i] = c < k ? *reinterpret_cast<const float4*>(w + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   float acc_bias = 0.f;
+#pragma unroll 2
   for (int64_t b = warp0; b < B; b += nw) {
     const float dl = dlogit[b];
     acc_bias += dl;
 #pragma unroll
-    for (int i = 0; i < MAXJ; ++i) {
-      const int j = lane + 32 * i;
-      if (j < k) {
-        float v = dl * w[j] * gelu_grad_f(to_f<T>(z[b * k + j]));
-        if (thresh != 0) v = drop_keep(k0, k1, (uint64_t)b * k + j, thresh) ? v * scale : 0.f;
-        const T o = from_f<T>(v);
-        dz[b * k + j] = o;
-        acc_b[i] += to_f<T>(o);
-        acc_w[i] = fmaf(dl, to_f<T>(a[b * k + j]), acc_w[i]);
+    for (int i = 0; i < MAXI; ++i) {
+      const int c = lane * 4 + 128 * i;
+      if (c < k) {
+        const float4 zv = gv_ld4<T>(z + b * k + c), av = gv_ld4<T>(a + b * k + c);
+        float4 v = make_float4(dl * wv[i].x * gelu_grad_f(zv.x), dl * wv[i].y * gelu_grad_f(zv.y),
+                               dl * wv[i].z * gelu_grad_f(zv.z), dl * wv[i].w * gelu_grad_f(zv.w));
+        if (thresh != 0) {
+          const uint64_t idx = (uint64_t)b * k + c;               // multiple of 4: two hash pairs
+          const uint32_t h0 = drop_hash(k0, k1, idx >> 1), h1 = drop_hash(k0, k1, (idx >> 1) + 1);
+          v.x = ((h0 & 0xFFFFu) >= thresh) ? v.x * scale : 0.f;
+          v.y = ((h0 >> 16) >= thresh) ? v.y * scale : 0.f;
+          v.z = ((h1 & 0xFFFFu) >= thresh) ? v.z * scale : 0.f;
+          v.w = ((h1 >> 16) >= thresh) ? v.w * scale : 0.f;
+        }
+        const float4 o = gv_st4<T>(dz + b * k + c, v);
+        acc_b[i].x += o.x; acc_b[i].y += o.y; acc_b[i].z += o.z; acc_b[i].w += o.w;
+        acc_w[i].x = fmaf(dl, av.x, acc_w[i].x); acc_w[i].y = fmaf(dl, av.y, acc_w[i].y);
+        acc_w[i].z = fmaf(dl, av.z, acc_w[i].z); acc_w[i].w = fmaf(dl, av.w, acc_w[i].w);
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < MAXJ; ++i) {
-    const int j = lane + 32 * i;
-    if (j < k) { atomicAdd(dw + j, acc_w[i]); atomicAdd(db_prev + j, acc_b[i]); }
+  for (int i = 0; i < MAXI; ++i) {
+    const int c = lane * 4 + 128 * i;
+    if (c < k) {
+      *reinterpret_cast<float4*>(&red[wib][0][c]) = acc_w[i];
+      *reinterpret_cast<float4*>(&red[wib][1][c]) = acc_b[i];
+    }
+  }
+  __syncthreads();                       // (every lane of a warp holds the same acc_bias: lane 0 reports it)
+  for (int e = threadIdx.x; e < 2 * k; e += 256) {
+    const int r = e / k, c = e - r * k;
+    float t = 0.f;
+#pragma unroll
+    for (int wv_ = 0; wv_ < 8; ++wv_) t += red[wv_][r][c];
+    atomicAdd((r == 0 ? dw : db_prev) + c, t);
   }
   if (lane == 0) atomicAdd(dbias, acc_bias);
 }

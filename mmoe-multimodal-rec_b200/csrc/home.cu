@@ -358,7 +358,7 @@ static int home_bwd_t(const mmoe_call* c, const mmoe_home_cfg* cfg, const float*
   // towers
   for (int k = 0; k < 2; ++k) {
     site_keys(c->seed, 30 + k, &k0, &k1);
-    gemv_bwd_kernel<T><<<rows_grid(B, 2), 256, 0, st>>>(dlogits + (size_t)k * B, (const T*)s.at + (size_t)k * B * th,
+    gemv_bwd_kernel<T><<<rows_grid(B, 4), 256, 0, st>>>(dlogits + (size_t)k * B, (const T*)s.at + (size_t)k * B * th,
                                                         (const T*)s.zt + (size_t)k * B * th, (const float*)P[ix.t_w2(k)],
                                                         (T*)t.dzt + (size_t)k * B * th, (float*)G[ix.t_w2(k)], (float*)G[ix.t_b2(k)],
                                                         (float*)G[ix.t_b1(k)], B, th, thresh, scale, k0, k1);
