@@ -428,7 +428,7 @@ def main():
     for j in range(2):
         done[j].record(cur)
 
-    loss_host = torch.empty(max(args.steps, 3), dtype=torch.float32).pin_memory()
+    loss_host = torch.empty(max(args.steps, 8), dtype=torch.float32).pin_memory()
 
     def e2e_loop(n):
         """Every step: its batch comes from pinned host memory (copied on the side stream while the previous step
