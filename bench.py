@@ -235,6 +235,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eval-mode", action="store_true", help="dropout off (debug)")
     ap.add_argument("--no-side-stream", action="store_true", help="run both fuse experts on the main stream")
+    ap.add_argument("--bucket-mb", type=int, default=25, help="DDP gradient bucket size")
     ap.add_argument("--nccl-ctas", type=int, default=0,
                     help="N>1: if > 0, cap NCCL at this many CTAs and keep as many SMs free of GEMM CTAs (measured: capping "
                          "lengthens the exposed part of the all-reduce at N=2; default leaves NCCL alone)")
@@ -287,7 +288,8 @@ def main():
         m.train(not args.eval_mode)
     if distributed:
         from torch.nn.parallel import DistributedDataParallel as DDP
-        cross_c, cui_c, cti_c, head_c = (DDP(m, device_ids=[local_rank], gradient_as_bucket_view=True) for m in (cross, cui, cti, head))
+        cross_c, cui_c, cti_c, head_c = (DDP(m, device_ids=[local_rank], gradient_as_bucket_view=True, bucket_cap_mb=args.bucket_mb)
+                                         for m in (cross, cui, cti, head))
     else:
         cross_c, cui_c, cti_c, head_c = cross, cui, cti, head
     pw_g = torch.tensor(858627.0 / 990303.0, device=dev)      # train.py:189-192
