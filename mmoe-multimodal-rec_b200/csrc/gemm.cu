@@ -93,6 +93,9 @@ struct alignas(64) TcParams {
   int total_tiles;
   int fmt;  // 0 f16, 1 bf16
   int bn;   // tile width of this launch: 256, or 128 / 64 when 256-wide tiles would leave most SMs idle
+  // dynamic tile scheduler (null = static round-robin): the launch's tile counter and its "units finished" counter
+  int* tile_counter;
+  int* done_counter;
 };
 
 struct SimtGroup {
@@ -315,6 +318,31 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v;
+}
+// wait with cluster-scope acquire: the data guarded by the barrier may have been written by the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  const long long t0 = clock64();
+  do {
+    if (clock64() - t0 > 4000000000ll) __trap();
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
 // TMA load issued by either CTA of the pair into ITS OWN shared memory, completing bytes on the leader's barrier
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
   asm volatile(
@@ -482,10 +510,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // ---- tile scheduler.  Static: tile = unit, unit + #units, ...  Dynamic (tile_counter != null): the leader's producer warp
+  // draws the next tile from a global counter and publishes it through a 2-slot ring (in both CTAs of a pair); every
+  // other role reads it from there.  A CTA that cannot be scheduled at once (an SM held by a communication kernel) then
+  // simply draws fewer tiles, instead of leaving its statically assigned share for a second wave.
+  const bool dyn = p.tile_counter != nullptr;
+  const uint32_t sched_base = bar_base + 144u;
+  auto tilefull_bar = [&](int s) { return sched_base + 8u * s; };
+  auto tileempty_bar = [&](int s) { return sched_base + 16u + 8u * s; };
+  auto ring_addr = [&](int s) { return sched_base + 32u + 4u * s; };
+  struct Sched { int cur; int slot; uint32_t phase; };
+  auto next_tile = [&](Sched& sc, bool writer) -> int {
+    if (!dyn) { const int t = sc.cur; sc.cur += tile_step; return t; }
+    int tile = 0;
+    if (writer) {
+      mbar_wait(tileempty_bar(sc.slot), sc.phase ^ 1u);          // every reader has taken the slot's previous tile
+      if (lane == 0) {
+        tile = atomicAdd(p.tile_counter, 1);
+        st_shared_u32(ring_addr(sc.slot), (uint32_t)tile);
+        if (CTAS == 2) {
+          st_cluster_u32(map_to_cta(ring_addr(sc.slot), 1u), (uint32_t)tile);
+          mbar_arrive_release_cluster(map_to_cta(tilefull_bar(sc.slot), 1u));
+        }
+        mbar_arrive(tilefull_bar(sc.slot));
+      }
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+    } else {
+      mbar_wait_cluster(tilefull_bar(sc.slot), sc.phase);
+      tile = (int)ld_shared_u32(ring_addr(sc.slot));
+      __syncwarp();
+      if (lane == 0) {
+        if (CTAS == 2 && crank != 0) mbar_arrive_cluster(map_to_cta(tileempty_bar(sc.slot), 0u)); else mbar_arrive(tileempty_bar(sc.slot));
+      }
+    }
+    if (++sc.slot == 2) { sc.slot = 0; sc.phase ^= 1u; }
+    return tile;
+  };
+
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     // the leader's tmem_empty collects the epilogue warps of BOTH CTAs
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), TC_EPI_WARPS * CTAS); }
+    // readers of a published tile: MMA warp + 8 epilogue warps in the leader, producer warp + 8 epilogue warps in the peer
+    for (int s = 0; s < 2; ++s) { mbar_init(tilefull_bar(s), 1); mbar_init(tileempty_bar(s), (TC_EPI_WARPS + 1) * CTAS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (CTAS == 2) cluster_sync_all();        // both CTAs' barriers exist before any remote arrival; also required before a pair allocation
@@ -513,7 +580,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       auto load = [&](uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
         if (CTAS == 2) tma_load_2d_pair(dst, map, bar, c0, c1); else tma_load_2d(dst, map, bar, c0, c1);
       };
-      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+      Sched sc{first_tile, 0, 0u};
+      for (int tile = next_tile(sc, crank == 0); tile < p.total_tiles; tile = next_tile(sc, crank == 0)) {
         const TileInfo t = decode_tile(p, tile);
         const TcGroup& g = p.g[t.gi];
         const int m0 = (t.m_blk * CTAS + (int)crank) * TBM, n0 = t.n_blk * BN + (int)crank * BN_CTA;
@@ -550,7 +618,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     if (crank == 0) {
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
-      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+      Sched sc{first_tile, 0, 0u};
+      for (int tile = next_tile(sc, false); tile < p.total_tiles; tile = next_tile(sc, false)) {
         const TileInfo t = decode_tile(p, tile);
         const TcGroup& g = p.g[t.gi];
         // instruction descriptor: D fp32, A/B f16|bf16, majors, N>>3, M>>4  (M = 256 across the pair)
@@ -608,7 +677,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     const int sub = lane >> 4;               // row of the pair this half-warp handles
     const int cl = (lane & 15) * 2;          // first of the lane's two columns inside a 32-column chunk
     int as = 0; uint32_t aphase = 0;
-    for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+    Sched sc{first_tile, 0, 0u};
+    for (int tile = next_tile(sc, false); tile < p.total_tiles; tile = next_tile(sc, false)) {
       const TileInfo t = decode_tile(p, tile);
       const TcGroup& g = p.g[t.gi];
       const EpiDev& E = g.epi;
@@ -858,6 +928,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   tc_fence_before();
   // pair: neither CTA may free TMEM or exit while the other can still signal its barriers or read its shared memory
   if (CTAS == 2) cluster_sync_all(); else __syncthreads();
+  if (dyn && threadIdx.x == 0 && crank == 0) {
+    // the unit that finishes last re-arms the launch's counters for their next use
+    const int units = (int)gridDim.x / CTAS;
+    if (atomicAdd(p.done_counter, 1) == units - 1) { atomicExch(p.tile_counter, 0); atomicExch(p.done_counter, 0); }
+  }
   if (warp == 2) {
     tc_fence_after();
     if (CTAS == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -1027,6 +1102,31 @@ static int launch_tc(const mmoe_gemm_problem* pr_in, int n, int dtype, cudaStrea
   }
   P.total_tiles = tiles;
   if (tiles == 0) return 0;
+  {
+    // dynamic tile scheduling: a ring of zeroed (tile, done) counter pairs per device; a launch takes the next pair and its
+    // last CTA zeroes it again (1024 launches later it is certainly free)
+    static const bool static_tiles = getenv("MMOE_STATIC_TILES") != nullptr;
+    constexpr int kSlots = 1024, kMaxDev = 16;
+    static int* counters[kMaxDev] = {};
+    static std::atomic<unsigned> seq[kMaxDev];
+    static std::mutex mu;
+    int dev = 0;
+    MMOE_CUDA(cudaGetDevice(&dev));
+    if (!static_tiles && dev >= 0 && dev < kMaxDev) {
+      if (counters[dev] == nullptr) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (counters[dev] == nullptr) {
+          int* ptr = nullptr;
+          MMOE_CUDA(cudaMalloc(&ptr, 2 * kSlots * sizeof(int)));
+          MMOE_CUDA(cudaMemset(ptr, 0, 2 * kSlots * sizeof(int)));
+          counters[dev] = ptr;
+        }
+      }
+      const unsigned slot = seq[dev].fetch_add(1u) % kSlots;
+      P.tile_counter = counters[dev] + slot;
+      P.done_counter = counters[dev] + kSlots + slot;
+    }
+  }
   using TcKernel = void (*)(const TcParams);
   static const TcKernel kernels[4][2] = {{gemm_tc_kernel<64, false, 1>, gemm_tc_kernel<64, true, 1>},
                                          {gemm_tc_kernel<128, false, 1>, gemm_tc_kernel<128, true, 1>},

@@ -91,7 +91,7 @@ class ParamPack:
 
 
 def _alloc_grads(params: Sequence[torch.Tensor], used: Sequence[bool]):
-    """One zeroed fp32 buffer holding the gradients of all used parameters; returns (views, pointer list)."""
+    """One zeroed fp32 buffer holding the gradients of all used parameters; returns (views, pointer list, flat buffer)."""
     total = sum(p.numel() + 64 for p, u in zip(params, used) if u)
     flat = torch.zeros(max(total, 1), dtype=torch.float32, device=params[0].device)
     views, ptrs, off = [], [], 0
@@ -104,7 +104,79 @@ def _alloc_grads(params: Sequence[torch.Tensor], used: Sequence[bool]):
         off += (p.numel() + 63) // 64 * 64
         views.append(v)
         ptrs.append(v.data_ptr())
-    return views, ptrs
+    return views, ptrs, flat
+
+
+# ----------------------------------------------------------------------------------------------
+# Data-parallel gradient exchange on the flat buffers
+# ----------------------------------------------------------------------------------------------
+class _GradSync:
+    """Averages gradients across the ranks of a process group, one collective per module (or encoder-layer stage)
+    backward: the backward functions already produce all of a module's parameter gradients in ONE contiguous fp32
+    buffer, so the exchange needs no per-parameter hooks, no bucket copies (DistributedDataParallel copies each of the
+    ~300 gradients into its buckets with a kernel of its own, ~1 ms per step of launch-bound work) and starts as soon
+    as the stage's gradients exist, overlapping the rest of the backward pass."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group)
+        self.avg = dist.get_backend(group) == "nccl"
+        self.pending = []
+
+    def reduce(self, flat: torch.Tensor):
+        if self.world == 1 or flat.numel() == 0:
+            return
+        if self.avg:
+            w = self.dist.all_reduce(flat, op=self.dist.ReduceOp.AVG, group=self.group, async_op=True)
+            self.pending.append((w, None))
+        else:                                   # gloo (CPU tests): no AVG
+            w = self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self.pending.append((w, flat))
+
+    def wait(self):
+        for w, t in self.pending:
+            w.wait()
+            if t is not None:
+                t.div_(self.world)
+        self.pending.clear()
+
+
+_GRAD_SYNC = None
+
+
+def enable_grad_allreduce(group=None):
+    """Turn on the gradient all-reduce of every native module's backward (call after init_process_group; instead of
+    wrapping the modules in DistributedDataParallel).  Call wait_grad_allreduce() after loss.backward()."""
+    global _GRAD_SYNC
+    _GRAD_SYNC = _GradSync(group)
+    return _GRAD_SYNC
+
+
+def disable_grad_allreduce():
+    global _GRAD_SYNC
+    _GRAD_SYNC = None
+
+
+def wait_grad_allreduce():
+    """Make the current stream wait for the gradient collectives issued during the last backward pass."""
+    if _GRAD_SYNC is not None:
+        _GRAD_SYNC.wait()
+
+
+def _sync_grads(flat: torch.Tensor):
+    if _GRAD_SYNC is not None:
+        _GRAD_SYNC.reduce(flat)
+
+
+def _span(flat: torch.Tensor, views, lo: int, hi: int):
+    """The contiguous slice of `flat` that holds views[lo:hi] (None entries skipped)."""
+    vs = [v for v in views[lo:hi] if v is not None]
+    if not vs:
+        return flat[0:0]
+    start = vs[0].storage_offset() - flat.storage_offset()
+    end = vs[-1].storage_offset() - flat.storage_offset() + vs[-1].numel()
+    return flat[start:end]
 
 
 def _bytes(n: int, device) -> torch.Tensor:
@@ -169,12 +241,13 @@ class HeadFn(torch.autograd.Function):
         pack, kind, cfg, training, drop_p, seed, dtype, ev, pt, saved, bwd, wb = ctx.state
         L = lib()
         B, dev = ev.shape[0], ev.device
-        views, gptrs = _alloc_grads(pt_shapes(pt, ctx), [True] * ctx.n_params)
+        views, gptrs, flat = _alloc_grads(pt_shapes(pt, ctx), [True] * ctx.n_params)
         work = _bytes(wb(C.byref(cfg), B, dtype), dev)
         d_ev = torch.empty_like(ev)
         dl = _f32c(dlogits)
         c = _call(dtype, B, training, 0, drop_p, seed, pt, gptrs, saved, work)
         check(bwd(C.byref(c), C.byref(cfg), ev.data_ptr(), dl.data_ptr(), d_ev.data_ptr()), kind + "_bwd")
+        _sync_grads(flat)
         grads = [v if req else None for v, req in zip(views, ctx.param_req)]
         return (None, None, None, None, None, None, d_ev.to(ctx.in_dtype), *grads)
 
@@ -220,13 +293,14 @@ class CrossFn(torch.autograd.Function):
         cfg, home, used, training, drop_p, seed, dtype, u, um, it, im, pt, saved = ctx.state
         L = lib()
         B, dev = u.shape[0], u.device
-        views, gptrs = _alloc_grads(pt, used)
+        views, gptrs, flat = _alloc_grads(pt, used)
         work = _bytes(L.mmoe_cross_workspace_bytes(C.byref(cfg), B, dtype), dev)
         d_user, d_item = torch.empty_like(u), torch.empty_like(it)
         do = _f32c(dout)
         c = _call(dtype, B, training, home, drop_p, seed, pt, gptrs, saved, work)
         check(L.mmoe_cross_bwd(C.byref(c), C.byref(cfg), u.data_ptr(), um.data_ptr(), it.data_ptr(), im.data_ptr(), do.data_ptr(),
                                d_user.data_ptr(), d_item.data_ptr()), "cross_bwd")
+        _sync_grads(flat)
         grads = [v if (req and v is not None) else None for v, req in zip(views, ctx.param_req)]
         return (None, None, None, None, None, None, d_user.to(ctx.in_dtypes[0]), None, d_item.to(ctx.in_dtypes[1]), None, *grads)
 
@@ -243,7 +317,7 @@ class CrossFn(torch.autograd.Function):
 class _CrossRun:
     """State shared by the stage nodes of one forward call."""
     __slots__ = ("cfg", "home", "training", "drop_p", "seed", "dtype", "u", "um", "it", "im", "pt", "saved",
-                 "views", "gptrs", "work", "d_user", "d_item")
+                 "views", "gptrs", "flat", "work", "d_user", "d_item")
 
 
 def _cross_stage_call(run: "_CrossRun", stage: int, dout_ptr):
@@ -271,6 +345,7 @@ class CrossLayerStage(torch.autograd.Function):
     def backward(ctx, _tok_grad):
         run = ctx.holder[0]
         _cross_stage_call(run, ctx.stage, None)
+        _sync_grads(_span(run.flat, run.views, ctx.idx0, ctx.idx0 + len(ctx.param_req)))    # this layer's 12 gradients
         grads = [run.views[ctx.idx0 + i] if req else None for i, req in enumerate(ctx.param_req)]
         if ctx.is_first:
             dx = (run.d_user if ctx.stage < 200 else run.d_item).to(ctx.x_dtype)
@@ -297,7 +372,7 @@ class CrossTailStage(torch.autograd.Function):
         run.pt = pack.tensors(all_params, run.dtype)
         run.saved = _bytes(L.mmoe_cross_saved_bytes(C.byref(cfg), B, run.dtype), dev)
         run.seed = _new_seed(training, drop_p)
-        run.views = run.gptrs = run.work = run.d_user = run.d_item = None
+        run.views = run.gptrs = run.flat = run.work = run.d_user = run.d_item = None
         out = torch.empty((B, cfg.d), dtype=torch.float32, device=dev)
         c = _call(run.dtype, B, training, home, drop_p, run.seed, run.pt, None, run.saved, None)
         check(L.mmoe_cross_fwd(C.byref(c), C.byref(cfg), run.u.data_ptr(), run.um.data_ptr(), run.it.data_ptr(), run.im.data_ptr(),
@@ -315,11 +390,15 @@ class CrossTailStage(torch.autograd.Function):
         run = ctx.holder[0]
         L = lib()
         B, dev = run.u.shape[0], run.u.device
-        run.views, run.gptrs = _alloc_grads(run.pt, ctx.used)
+        run.views, run.gptrs, run.flat = _alloc_grads(run.pt, ctx.used)
         run.work = _bytes(L.mmoe_cross_workspace_bytes(C.byref(run.cfg), B, run.dtype), dev)
         run.d_user, run.d_item = torch.empty_like(run.u), torch.empty_like(run.it)
         do = _f32c(dout)
         _cross_stage_call(run, 0, do.data_ptr())
+        # gate (first parameter) and everything after the two encoder stacks are final after this stage
+        n_enc = 24 * run.cfg.n_layer
+        _sync_grads(_span(run.flat, run.views, 0, 1))
+        _sync_grads(_span(run.flat, run.views, 1 + n_enc, len(run.views)))
         grads = [run.views[i] if (req and run.views[i] is not None) else None for i, req in zip(ctx.tail_idx, ctx.param_req)]
         empty = dout.new_empty(0)
         return (None,) * 9 + (None, None, None, None, empty, empty, *grads)
@@ -378,12 +457,13 @@ class FuseFn(torch.autograd.Function):
     def backward(ctx, dout):
         cfg, home, used, training, drop_p, seed, dtype, B, dev, pt, saved = ctx.state
         L = lib()
-        views, gptrs = _alloc_grads(pt, used)
+        views, gptrs, flat = _alloc_grads(pt, used)
         work = _bytes(L.mmoe_fuse_workspace_bytes(C.byref(cfg), B, dtype), dev)
         d_cat = torch.empty((B, 2, cfg.d), dtype=torch.float32, device=dev)
         do = _f32c(dout)
         c = _call(dtype, B, training, home, drop_p, seed, pt, gptrs, saved, work)
         check(L.mmoe_fuse_bwd(C.byref(c), C.byref(cfg), do.data_ptr(), d_cat.data_ptr()), "fuse_bwd")
+        _sync_grads(flat)
         grads = [v if (req and v is not None) else None for v, req in zip(views, ctx.param_req)]
         return (None, None, None, None, None, None, d_cat[:, 0].to(ctx.in_dtypes[0]), d_cat[:, 1].to(ctx.in_dtypes[1]), *grads)
 
@@ -423,12 +503,14 @@ class ImgPoolFn(torch.autograd.Function):
         L = lib()
         B, n_tok, d = shape
         dev = dout.device
-        dg, db = torch.zeros_like(g), torch.zeros_like(b)
+        flat = torch.zeros(g.numel() + b.numel(), dtype=torch.float32, device=dev)
+        dg, db = flat[:g.numel()].view(g.shape), flat[g.numel():].view(b.shape)
         d_tok = torch.empty(shape, dtype=tk_dtype, device=dev) if ctx.needs_tokens else None
         do = _f32c(dout)
         c = _call(F32, B, training, 0, drop_p, seed, [g, b], [dg.data_ptr(), db.data_ptr()], None, None)
         check(L.mmoe_img_pool_bwd(C.byref(c), n_tok, d, int(pool_cls), stats.data_ptr(), pooled.data_ptr(), do.data_ptr(),
                                   d_tok.data_ptr() if d_tok is not None else None, _TORCH2MMOE[tk_dtype]), "img_pool_bwd")
+        _sync_grads(flat)
         return None, None, None, (d_tok.to(in_dtype) if d_tok is not None else None), dg, db
 
 
@@ -457,11 +539,12 @@ class ImgProjFn(torch.autograd.Function):
     def backward(ctx, dout):
         d, proj, dtype, B, dev, pt, saved = ctx.state
         L = lib()
-        views, gptrs = _alloc_grads(pt, [True] * len(pt))
+        views, gptrs, flat = _alloc_grads(pt, [True] * len(pt))
         work = _bytes(L.mmoe_img_proj_workspace_bytes(B, d, proj, dtype), dev)
         dx = torch.empty((B, d), dtype=torch.float32, device=dev)
         do = _f32c(dout)
         c = _call(dtype, B, False, 0, 0.0, 0, pt, gptrs, saved, work)
         check(L.mmoe_img_proj_bwd(C.byref(c), d, proj, do.data_ptr(), dx.data_ptr()), "img_proj_bwd")
+        _sync_grads(flat)
         grads = [v if req else None for v, req in zip(views, ctx.param_req)]
         return (None, None, None, dx.to(ctx.in_dtype), *grads)

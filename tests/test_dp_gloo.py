@@ -50,3 +50,42 @@ def test_sharded_gradients_average_to_full_batch_gradient():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert err < 1e-12
+
+
+def _sync_worker(rank, world, port, q):
+    """The native exchange (functional._GradSync) on CPU tensors: flat buffers and sub-spans are averaged over ranks."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import mmoe_multimodal_rec_b200 as pkg
+    Fn = pkg.functional
+    sync = Fn.enable_grad_allreduce()
+    params = [torch.zeros(3, 5), torch.zeros(7), torch.zeros(2, 2)]
+    views, _ptrs, flat = Fn._alloc_grads(params, [True, False, True])
+    assert views[1] is None and flat.numel() >= 15 + 4
+    views[0].fill_(float(rank + 1))
+    views[2].fill_(10.0 * (rank + 1))
+    Fn._sync_grads(Fn._span(flat, views, 0, 1))       # one stage's span ...
+    Fn._sync_grads(Fn._span(flat, views, 1, 3))       # ... and the rest (skips the unused parameter)
+    assert len(sync.pending) == 2
+    Fn.wait_grad_allreduce()
+    ok = bool(torch.all(views[0] == 1.5)) and bool(torch.all(views[2] == 15.0)) and not sync.pending
+    Fn.disable_grad_allreduce()
+    Fn._sync_grads(flat)                               # off: no collective issued
+    if rank == 0:
+        q.put(ok)
+    dist.destroy_process_group()
+
+
+def test_native_flat_buffer_gradient_allreduce():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_sync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok
