@@ -1103,9 +1103,11 @@ static int launch_tc(const mmoe_gemm_problem* pr_in, int n, int dtype, cudaStrea
   P.total_tiles = tiles;
   if (tiles == 0) return 0;
   {
-    // dynamic tile scheduling: a ring of zeroed (tile, done) counter pairs per device; a launch takes the next pair and its
-    // last CTA zeroes it again (1024 launches later it is certainly free)
-    static const bool static_tiles = getenv("MMOE_STATIC_TILES") != nullptr;
+    // dynamic tile scheduling (opt-in: MMOE_DYNAMIC_TILES=1): a ring of zeroed (tile, done) counter pairs per device; a
+    // launch takes the next pair and its last CTA zeroes it again (1024 launches later it is certainly free).  Measured:
+    // 1.2 % slower than the static round-robin on an otherwise idle GPU (9.90 -> 10.02 ms/step) and no gain next to NCCL
+    // at N = 2 (10.94 vs 10.96 ms/step), so the static order (longest tiles first) stays the default.
+    static const bool static_tiles = getenv("MMOE_DYNAMIC_TILES") == nullptr;
     constexpr int kSlots = 1024, kMaxDev = 16;
     static int* counters[kMaxDev] = {};
     static std::atomic<unsigned> seq[kMaxDev];
