@@ -12,8 +12,10 @@ stack -> TwoTaskMMoE -> 2x BCEWithLogits -> backward.  Modules are in train() mo
 training).  Synthetic inputs of the shapes the encoders produce (sentence vectors [B,64,768] + masks, doc
 vectors, ViT tokens [B,197,768]) and random-init weights; the text encoders / ViT backbone are the reference's
 own torch modules and are not part of the timed path (north_star: "timed separately").
-For N > 1 each rank runs the same per-GPU batch (weak scaling) and the gradients of the four trainable modules
-are all-reduced by DistributedDataParallel over NCCL, overlapped with backward.
+For N > 1 each rank runs the same per-GPU batch (weak scaling) and the gradients are averaged over NCCL, overlapped with
+backward: by the package's native flat-buffer exchange (default) or by DistributedDataParallel wrappers (--ddp).
+The headline pass carries no per-launch events; the GEMM roofline is measured in a second, single-stream pass of the
+same steps with a CUDA event pair around every GEMM launch.
 
 One JSON line on stdout (rank 0); see README / DESIGN.md for the keys.
 """
