@@ -215,7 +215,7 @@ def run_reference_arm(args, rank, world):
 def workload_config(B, n_gpus):
     return {"workload": "v1 MMoE fusion-and-head path fwd+bwd (ItemImageExpert tail + RobustTextCrossExpert + 2x EnhancedCrossFuse "
                         "+ TwoTaskMMoE + BCE), train mode, BASELINE configs[1]",
-            "per_gpu_batch": B, "global_batch": B * n_gpus, "sentences": S, "d_model": D, "parallelism": f"dp{n_gpus}",
+            "per_gpu_batch": B, "global_batch": B * n_gpus, "sentences": S, "vector_dim": D, "parallelism": f"dp{n_gpus}",
             "autocast": "bf16", "l2": "inputs (~0.5 GB/step) and activations (~3 GB) exceed the 126 MB L2; no flush needed",
             "encoders": "text encoders / ViT backbone excluded (reference torch modules, timed separately)",
             "streams": "the two EnhancedCrossFuse experts run on side streams next to the cross expert"}
@@ -514,7 +514,11 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 grouped GEMM, all launches of the timed region)",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": None,
+                         "traffic_note": "aggregate over 88 launches, so no single per-launch figure; ncu --set full of the FFN1 "
+                                         "768->3072 launch: 55 MB read + 147 MB written vs 255 MB algorithmic "
+                                         "(profiles/r01_gemm_final_ncu_full.md)",
+                         "peak_source": peak_src,
                          "gemm_ms_per_step": g_ms.value / args.steps, "gemm_launches_per_step": g_n.value / args.steps,
                          "measured_over": "a second pass of the same K steps, single stream, with an event pair around every GEMM launch",
                          "ms_per_step_with_events": ms_total_ev / args.steps,
