@@ -115,17 +115,29 @@ class _GradSync:
     backward: the backward functions already produce all of a module's parameter gradients in ONE contiguous fp32
     buffer, so the exchange needs no per-parameter hooks, no bucket copies (DistributedDataParallel copies each of the
     ~300 gradients into its buckets with a kernel of its own, ~1 ms per step of launch-bound work) and starts as soon
-    as the stage's gradients exist, overlapping the rest of the backward pass."""
+    as the stage's gradients exist, overlapping the rest of the backward pass.
+
+    Ownership rule (what makes the averaged values the ones that end up in ``.grad``): while the exchange is on, a
+    backward function does NOT return its parameter gradients to autograd.  It keeps the flat buffer, starts the
+    in-place collective on it, and registers the (parameter, view) pairs here.  ``finish()`` — queued on the autograd
+    engine so that it runs when the backward pass ends, exactly where DDP finalises its buckets — first makes the
+    compute stream wait for every collective and only then installs the views: ``p.grad = view`` when the parameter
+    has no gradient yet (no copy: ``.grad`` aliases the reduced buffer), ``p.grad += view`` when it has one
+    (gradient accumulation, ``zero_grad(set_to_none=False)``).  Nothing reads or copies a buffer while NCCL is still
+    reducing it."""
 
     def __init__(self, group=None):
         import torch.distributed as dist
         self.dist, self.group = dist, group
         self.world = dist.get_world_size(group)
         self.avg = dist.get_backend(group) == "nccl"
-        self.pending = []
+        self.sync = True             # False = accumulate locally (the equivalent of DDP.no_sync())
+        self.pending = []            # (work, tensor to divide afterwards or None)
+        self.deferred = []           # (params, views, flat): installed into .grad by finish()
+        self.callback_queued = False
 
     def reduce(self, flat: torch.Tensor):
-        if self.world == 1 or flat.numel() == 0:
+        if self.world == 1 or flat.numel() == 0 or not self.sync:
             return
         if self.avg:
             w = self.dist.all_reduce(flat, op=self.dist.ReduceOp.AVG, group=self.group, async_op=True)
@@ -134,6 +146,17 @@ class _GradSync:
             w = self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True)
             self.pending.append((w, flat))
 
+    def defer(self, params, views, flat):
+        """Hand the gradients of `params` (views of `flat`) over for installation at the end of the backward pass."""
+        self.deferred.append((list(params), list(views), flat))
+        if not self.callback_queued:
+            self.callback_queued = True
+            try:
+                torch.autograd.Variable._execution_engine.queue_callback(self.finish)
+            except RuntimeError:
+                # not inside a backward pass (direct call in a test): the caller runs wait_grad_allreduce()
+                self.callback_queued = False
+
     def wait(self):
         for w, t in self.pending:
             w.wait()
@@ -141,13 +164,47 @@ class _GradSync:
                 t.div_(self.world)
         self.pending.clear()
 
+    def finish(self):
+        self.callback_queued = False
+        self.wait()
+        for params, views, flat in self.deferred:
+            _install_grads(params, views, flat)
+        self.deferred.clear()
+
+
+def _install_grads(params, views, flat):
+    """p.grad = view (aliasing `flat`) or p.grad += view; one fused add when every .grad still aliases the previous
+    flat buffer of the same layout (the usual gradient-accumulation case)."""
+    live = [(p, v) for p, v in zip(params, views) if v is not None and p is not None]
+    if not live:
+        return
+    if all(p.grad is None for p, _ in live):
+        for p, v in live:
+            p.grad = v
+            p._mmoe_grad_flat = flat
+        return
+    prev = getattr(live[0][0], "_mmoe_grad_flat", None)
+    if (prev is not None and prev.shape == flat.shape and prev.device == flat.device and
+            all(p.grad is not None and getattr(p, "_mmoe_grad_flat", None) is prev and p.grad.shape == v.shape and
+                p.grad.is_contiguous() and p.grad.data_ptr() - prev.data_ptr() == v.data_ptr() - flat.data_ptr()
+                for p, v in live)):
+        prev.add_(flat)
+        return
+    for p, v in live:
+        if p.grad is None:
+            p.grad = v.clone()
+        else:
+            p.grad.add_(v)
+        p._mmoe_grad_flat = None
+
 
 _GRAD_SYNC = None
 
 
 def enable_grad_allreduce(group=None):
     """Turn on the gradient all-reduce of every native module's backward (call after init_process_group; instead of
-    wrapping the modules in DistributedDataParallel).  Call wait_grad_allreduce() after loss.backward()."""
+    wrapping the modules in DistributedDataParallel).  The averaged gradients are in ``.grad`` when ``backward()``
+    returns; ``wait_grad_allreduce()`` is kept for explicit use outside a backward pass."""
     global _GRAD_SYNC
     _GRAD_SYNC = _GradSync(group)
     return _GRAD_SYNC
@@ -158,15 +215,64 @@ def disable_grad_allreduce():
     _GRAD_SYNC = None
 
 
-def wait_grad_allreduce():
-    """Make the current stream wait for the gradient collectives issued during the last backward pass."""
+def set_grad_sync(on: bool):
+    """on=False: the following backward passes accumulate locally without communicating (DDP.no_sync() equivalent);
+    on=True: the next backward all-reduces what it produces.  Because the all-reduce is linear, the usual pattern —
+    no_sync on all but the last micro-step — needs the accumulated buffer reduced once: call
+    ``allreduce_accumulated(modules)`` after the last micro-step instead of re-enabling the per-stage exchange."""
     if _GRAD_SYNC is not None:
-        _GRAD_SYNC.wait()
+        _GRAD_SYNC.sync = bool(on)
+
+
+def allreduce_accumulated(modules):
+    """Average the accumulated ``.grad`` of the given native modules across ranks: one collective per flat buffer
+    whose views are still the parameters' gradients, one per parameter otherwise.  For gradient accumulation with
+    set_grad_sync(False) on all micro-steps."""
+    gs = _GRAD_SYNC
+    if gs is None or gs.world == 1:
+        return
+    was = gs.sync
+    gs.sync = True
+    try:
+        seen = set()
+        for m in modules:
+            for p in m.parameters():
+                if p.grad is None:
+                    continue
+                flat = getattr(p, "_mmoe_grad_flat", None)
+                inside = flat is not None and 0 <= p.grad.data_ptr() - flat.data_ptr() <= (flat.numel() - p.grad.numel()) * 4
+                if inside:
+                    if id(flat) not in seen:
+                        seen.add(id(flat))
+                        gs.reduce(flat)
+                else:
+                    gs.reduce(p.grad)
+        gs.wait()
+    finally:
+        gs.sync = was
+
+
+def wait_grad_allreduce():
+    """Make the current stream wait for the gradient collectives issued so far and install their results in ``.grad``
+    (done automatically at the end of a backward pass)."""
+    if _GRAD_SYNC is not None:
+        _GRAD_SYNC.finish()
 
 
 def _sync_grads(flat: torch.Tensor):
     if _GRAD_SYNC is not None:
         _GRAD_SYNC.reduce(flat)
+
+
+def _hand_over(params, views, req, flat):
+    """What a backward function returns for its parameters.  Exchange off: the views themselves (autograd /
+    DistributedDataParallel take it from there; no other reference to them is kept, so AccumulateGrad adopts them
+    without a copy).  Exchange on: None for every parameter — the views go to _GradSync.defer (see its docstring)."""
+    out = [v if (r and v is not None) else None for v, r in zip(views, req)]
+    if _GRAD_SYNC is None:
+        return out
+    _GRAD_SYNC.defer([p if o is not None else None for p, o in zip(params, out)], out, flat)
+    return [None] * len(out)
 
 
 def _span(flat: torch.Tensor, views, lo: int, hi: int):
@@ -177,6 +283,13 @@ def _span(flat: torch.Tensor, views, lo: int, hi: int):
     start = vs[0].storage_offset() - flat.storage_offset()
     end = vs[-1].storage_offset() - flat.storage_offset() + vs[-1].numel()
     return flat[start:end]
+
+
+def _state(ctx):
+    if ctx.state is None:
+        raise RuntimeError("mmoe_b200: backward called twice over the same graph; the saved activations are released "
+                           "at the end of the first backward pass (retain_graph is not supported)")
+    return ctx.state
 
 
 def _bytes(n: int, device) -> torch.Tensor:
@@ -228,6 +341,7 @@ class HeadFn(torch.autograd.Function):
         check(fwd(C.byref(c), C.byref(cfg), ev.data_ptr(), logits.data_ptr(), gates.data_ptr() if want_gates else None), kind + "_fwd")
         ctx.state = (pack, kind, cfg, training, drop_p, seed, dtype, ev, pt, saved, bwd, wb)
         ctx.n_params = len(params)
+        ctx.params = params
         ctx.param_req = [p.requires_grad for p in params]
         ctx.in_dtype = expert_vecs.dtype
         ctx.mark_non_differentiable(*( [gates] if want_gates else [] ))
@@ -238,23 +352,19 @@ class HeadFn(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, dlogits, *unused):
-        pack, kind, cfg, training, drop_p, seed, dtype, ev, pt, saved, bwd, wb = ctx.state
+        pack, kind, cfg, training, drop_p, seed, dtype, ev, pt, saved, bwd, wb = _state(ctx)
         L = lib()
         B, dev = ev.shape[0], ev.device
-        views, gptrs, flat = _alloc_grads(pt_shapes(pt, ctx), [True] * ctx.n_params)
+        views, gptrs, flat = _alloc_grads(pt, [True] * ctx.n_params)
         work = _bytes(wb(C.byref(cfg), B, dtype), dev)
         d_ev = torch.empty_like(ev)
         dl = _f32c(dlogits)
         c = _call(dtype, B, training, 0, drop_p, seed, pt, gptrs, saved, work)
         check(bwd(C.byref(c), C.byref(cfg), ev.data_ptr(), dl.data_ptr(), d_ev.data_ptr()), kind + "_bwd")
         _sync_grads(flat)
-        grads = [v if req else None for v, req in zip(views, ctx.param_req)]
+        grads = _hand_over(ctx.params, views, ctx.param_req, flat)
+        ctx.state = ctx.params = None           # release the saved blob / inputs / 16-bit weights with the pass
         return (None, None, None, None, None, None, d_ev.to(ctx.in_dtype), *grads)
-
-
-def pt_shapes(pt, ctx):
-    """fp32 gradient buffers have the shapes of the parameters (pt holds same-shaped tensors)."""
-    return pt
 
 
 # ----------------------------------------------------------------------------------------------
@@ -283,6 +393,7 @@ class CrossFn(torch.autograd.Function):
         if DEBUG_SAVED is not None:
             DEBUG_SAVED.append(("cross", cfg, home, B, dtype, saved))
         ctx.state = (cfg, home, list(used), training, drop_p, seed, dtype, u, um, it, im, pt, saved)
+        ctx.params = params
         ctx.param_req = [p.requires_grad for p in params]
         ctx.in_dtypes = (user.dtype, item.dtype)
         return out
@@ -290,7 +401,7 @@ class CrossFn(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
-        cfg, home, used, training, drop_p, seed, dtype, u, um, it, im, pt, saved = ctx.state
+        cfg, home, used, training, drop_p, seed, dtype, u, um, it, im, pt, saved = _state(ctx)
         L = lib()
         B, dev = u.shape[0], u.device
         views, gptrs, flat = _alloc_grads(pt, used)
@@ -301,7 +412,8 @@ class CrossFn(torch.autograd.Function):
         check(L.mmoe_cross_bwd(C.byref(c), C.byref(cfg), u.data_ptr(), um.data_ptr(), it.data_ptr(), im.data_ptr(), do.data_ptr(),
                                d_user.data_ptr(), d_item.data_ptr()), "cross_bwd")
         _sync_grads(flat)
-        grads = [v if (req and v is not None) else None for v, req in zip(views, ctx.param_req)]
+        grads = _hand_over(ctx.params, views, ctx.param_req, flat)
+        ctx.state = ctx.params = None
         return (None, None, None, None, None, None, d_user.to(ctx.in_dtypes[0]), None, d_item.to(ctx.in_dtypes[1]), None, *grads)
 
 
@@ -317,7 +429,21 @@ class CrossFn(torch.autograd.Function):
 class _CrossRun:
     """State shared by the stage nodes of one forward call."""
     __slots__ = ("cfg", "home", "training", "drop_p", "seed", "dtype", "u", "um", "it", "im", "pt", "saved",
-                 "views", "gptrs", "flat", "work", "d_user", "d_item")
+                 "views", "gptrs", "flat", "work", "d_user", "d_item", "stages_left")
+
+
+def _run_of(ctx):
+    if not ctx.holder:
+        raise RuntimeError("mmoe_b200: backward through a RobustTextCrossExpert call whose buffers were already released "
+                           "(a second backward over the same graph is not supported)")
+    return ctx.holder[0]
+
+
+def _stage_done(holder, run):
+    """The last stage of a backward pass releases the activations, the workspace and the gradient buffer references."""
+    run.stages_left -= 1
+    if run.stages_left <= 0:
+        holder.clear()
 
 
 def _cross_stage_call(run: "_CrossRun", stage: int, dout_ptr):
@@ -335,6 +461,7 @@ class CrossLayerStage(torch.autograd.Function):
     @staticmethod
     def forward(ctx, holder, stage: int, idx0: int, x, *layer_params):
         ctx.holder, ctx.stage, ctx.idx0 = holder, stage, idx0
+        ctx.params = layer_params
         ctx.param_req = [p.requires_grad for p in layer_params]
         ctx.is_first = (stage % 100) == 0
         ctx.x_dtype = x.dtype
@@ -343,14 +470,23 @@ class CrossLayerStage(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, _tok_grad):
-        run = ctx.holder[0]
+        run = _run_of(ctx)
         _cross_stage_call(run, ctx.stage, None)
-        _sync_grads(_span(run.flat, run.views, ctx.idx0, ctx.idx0 + len(ctx.param_req)))    # this layer's 12 gradients
-        grads = [run.views[ctx.idx0 + i] if req else None for i, req in enumerate(ctx.param_req)]
+        lo, hi = ctx.idx0, ctx.idx0 + len(ctx.param_req)
+        span = _span(run.flat, run.views, lo, hi)                     # this layer's 12 gradients
+        _sync_grads(span)
+        # the views leave `run` with this stage: nothing else may keep a reference to a gradient that autograd (or the
+        # exchange) now owns — AccumulateGrad only adopts a tensor nobody else holds
+        views = run.views[lo:hi]
+        run.views[lo:hi] = [None] * (hi - lo)
+        grads = _hand_over(ctx.params, views, ctx.param_req, span)
+        del views
         if ctx.is_first:
             dx = (run.d_user if ctx.stage < 200 else run.d_item).to(ctx.x_dtype)
         else:
             dx = _tok_grad.new_empty(0)
+        ctx.params = None
+        _stage_done(ctx.holder, run)
         return (None, None, None, dx, *grads)
 
 
@@ -380,14 +516,16 @@ class CrossTailStage(torch.autograd.Function):
         if DEBUG_SAVED is not None:
             DEBUG_SAVED.append(("cross", cfg, home, B, run.dtype, run.saved))
         holder.append(run)
+        run.stages_left = 2 * cfg.n_layer + 1
         ctx.holder, ctx.used, ctx.tail_idx = holder, list(used), list(tail_idx)
+        ctx.params = tail_params
         ctx.param_req = [p.requires_grad for p in tail_params]
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
-        run = ctx.holder[0]
+        run = _run_of(ctx)
         L = lib()
         B, dev = run.u.shape[0], run.u.device
         run.views, run.gptrs, run.flat = _alloc_grads(run.pt, ctx.used)
@@ -397,10 +535,22 @@ class CrossTailStage(torch.autograd.Function):
         _cross_stage_call(run, 0, do.data_ptr())
         # gate (first parameter) and everything after the two encoder stacks are final after this stage
         n_enc = 24 * run.cfg.n_layer
-        _sync_grads(_span(run.flat, run.views, 0, 1))
-        _sync_grads(_span(run.flat, run.views, 1 + n_enc, len(run.views)))
-        grads = [run.views[i] if (req and run.views[i] is not None) else None for i, req in zip(ctx.tail_idx, ctx.param_req)]
+        n_all = len(run.views)
+        grads = [None] * len(ctx.tail_idx)
+        pos = {i: j for j, i in enumerate(ctx.tail_idx)}
+        for lo, hi in ((0, 1), (1 + n_enc, n_all)):
+            span = _span(run.flat, run.views, lo, hi)
+            _sync_grads(span)
+            idx = [i for i in range(lo, hi) if i in pos]
+            views = [run.views[i] for i in idx]
+            run.views[lo:hi] = [None] * (hi - lo)
+            out = _hand_over([ctx.params[pos[i]] for i in idx], views, [ctx.param_req[pos[i]] for i in idx], span)
+            del views
+            for i, g in zip(idx, out):
+                grads[pos[i]] = g
         empty = dout.new_empty(0)
+        ctx.params = None
+        _stage_done(ctx.holder, run)
         return (None,) * 9 + (None, None, None, None, empty, empty, *grads)
 
 
@@ -448,6 +598,7 @@ class FuseFn(torch.autograd.Function):
         if DEBUG_SAVED is not None:
             DEBUG_SAVED.append(("fuse", cfg, home, B, dtype, saved))
         ctx.state = (cfg, home, list(used), training, drop_p, seed, dtype, B, dev, pt, saved)
+        ctx.params = params
         ctx.param_req = [p.requires_grad for p in params]
         ctx.in_dtypes = (v_cls.dtype, t_cls.dtype)
         return out
@@ -455,7 +606,7 @@ class FuseFn(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
-        cfg, home, used, training, drop_p, seed, dtype, B, dev, pt, saved = ctx.state
+        cfg, home, used, training, drop_p, seed, dtype, B, dev, pt, saved = _state(ctx)
         L = lib()
         views, gptrs, flat = _alloc_grads(pt, used)
         work = _bytes(L.mmoe_fuse_workspace_bytes(C.byref(cfg), B, dtype), dev)
@@ -464,7 +615,8 @@ class FuseFn(torch.autograd.Function):
         c = _call(dtype, B, training, home, drop_p, seed, pt, gptrs, saved, work)
         check(L.mmoe_fuse_bwd(C.byref(c), C.byref(cfg), do.data_ptr(), d_cat.data_ptr()), "fuse_bwd")
         _sync_grads(flat)
-        grads = [v if (req and v is not None) else None for v, req in zip(views, ctx.param_req)]
+        grads = _hand_over(ctx.params, views, ctx.param_req, flat)
+        ctx.state = ctx.params = None
         return (None, None, None, None, None, None, d_cat[:, 0].to(ctx.in_dtypes[0]), d_cat[:, 1].to(ctx.in_dtypes[1]), *grads)
 
 
@@ -493,13 +645,14 @@ class ImgPoolFn(torch.autograd.Function):
         check(L.mmoe_img_pool_fwd(C.byref(c), tk.data_ptr(), _TORCH2MMOE[tk.dtype], n_tok, d, int(pool_cls), out.data_ptr(),
                                   stats.data_ptr(), pooled.data_ptr()), "img_pool_fwd")
         ctx.state = (pool_cls, training, drop_p, seed, g, b, stats, pooled, tk.dtype, tuple(tk.shape), tokens.dtype)
+        ctx.params = (gamma, beta)
         ctx.needs_tokens = tokens.requires_grad
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
-        pool_cls, training, drop_p, seed, g, b, stats, pooled, tk_dtype, shape, in_dtype = ctx.state
+        pool_cls, training, drop_p, seed, g, b, stats, pooled, tk_dtype, shape, in_dtype = _state(ctx)
         L = lib()
         B, n_tok, d = shape
         dev = dout.device
@@ -511,6 +664,8 @@ class ImgPoolFn(torch.autograd.Function):
         check(L.mmoe_img_pool_bwd(C.byref(c), n_tok, d, int(pool_cls), stats.data_ptr(), pooled.data_ptr(), do.data_ptr(),
                                   d_tok.data_ptr() if d_tok is not None else None, _TORCH2MMOE[tk_dtype]), "img_pool_bwd")
         _sync_grads(flat)
+        dg, db = _hand_over(ctx.params, [dg, db], [p.requires_grad for p in ctx.params], flat)
+        ctx.state = ctx.params = None
         return None, None, None, (d_tok.to(in_dtype) if d_tok is not None else None), dg, db
 
 
@@ -530,6 +685,7 @@ class ImgProjFn(torch.autograd.Function):
         c = _call(dtype, B, False, 0, 0.0, 0, pt, None, saved, None)
         check(L.mmoe_img_proj_fwd(C.byref(c), d, proj, x.data_ptr(), out.data_ptr()), "img_proj_fwd")
         ctx.state = (d, proj, dtype, B, dev, pt, saved)
+        ctx.params = params
         ctx.param_req = [p.requires_grad for p in params]
         ctx.in_dtype = img_vec.dtype
         return out
@@ -537,7 +693,7 @@ class ImgProjFn(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
-        d, proj, dtype, B, dev, pt, saved = ctx.state
+        d, proj, dtype, B, dev, pt, saved = _state(ctx)
         L = lib()
         views, gptrs, flat = _alloc_grads(pt, [True] * len(pt))
         work = _bytes(L.mmoe_img_proj_workspace_bytes(B, d, proj, dtype), dev)
@@ -546,5 +702,6 @@ class ImgProjFn(torch.autograd.Function):
         c = _call(dtype, B, False, 0, 0.0, 0, pt, gptrs, saved, work)
         check(L.mmoe_img_proj_bwd(C.byref(c), d, proj, do.data_ptr(), dx.data_ptr()), "img_proj_bwd")
         _sync_grads(flat)
-        grads = [v if req else None for v, req in zip(views, ctx.param_req)]
+        grads = _hand_over(ctx.params, views, ctx.param_req, flat)
+        ctx.state = ctx.params = None
         return (None, None, None, dx.to(ctx.in_dtype), *grads)
