@@ -114,6 +114,12 @@ int mmoe_gemm_grouped(const mmoe_gemm_problem* problems /*host*/, int n_problems
 int mmoe_gemm_timing(int enable);
 int mmoe_gemm_timing_read(double* total_ms, double* total_flops, int64_t* launches, int tc_only);
 
+/* Launch trace of the tensor-core GEMM launches (tests: which kernel variant a shape resolved to).  enable != 0 clears the
+ * record and starts recording, 0 stops.  _read copies up to max_entries records of 4 ints {tile width, CTAs per tile (2 =
+ * cta_group::2 pair kernel), rich epilogue, tiles} into out (may be NULL) and returns the number recorded so far. */
+int mmoe_launch_trace(int enable);
+int mmoe_launch_trace_read(int32_t* out, int max_entries);
+
 /* Number of SMs the persistent GEMM leaves free (its CTAs own a whole SM each and cannot co-reside with a running
  * NCCL kernel).  Set it to the number of NCCL CTAs when gradient all-reduce overlaps backward; default 0 or the
  * environment variable MMOE_SM_RESERVE. */
@@ -121,6 +127,19 @@ int mmoe_set_sm_reserve(int n_sms);
 
 /* keep-mask a kernel would use for flat element index i in [0,n): out[i] = 1/0 (uint8). */
 int mmoe_dropout_mask(uint32_t key0, uint32_t key1, float p, int64_t n, uint8_t* out, void* stream);
+/* Keys of dropout site `site` of a module call made with mmoe_call.seed = seed (host function).  Site numbers, with the
+ * tensor whose row-major flat index the mask is taken over (the reference's nn.Dropout call sites in brackets):
+ *   encoder layer l (model.py:207-212 / :460-465; stack base s0 = 16*l, +8 for the item stack of the cross expert):
+ *     s0+0 attention probabilities [B,H,Sq,Sk] (MHA dropout), s0+1 dropout1 [B*S,d], s0+2 FFN dropout [B*S,4d],
+ *     s0+3 dropout2 [B*S,d];
+ *   RobustTextCrossExpert: 100 cross-attention probabilities [B,H,S,S] (model.py:407-408), 101 AttnPool1D weights [B,S]
+ *     (:197,204), 102 mlp[2] [B,4d], 103 mlp[4] [B,d] (:421-423);
+ *   EnhancedCrossFuse: 100 proj[3] [B,d] (model.py:488);
+ *   TwoTaskMMoE: 10+t tower_t[3] [B,hidden], 20+t tower_t[6] [B,hidden/2] (model.py:545-556; t = 0 good, 1 best);
+ *   HOME_MMoE_Complete: 10+e ExpertMLP e dropout [B,1024] (model_HoME.py:33; e: meta 0..n_shared-1, then good, then best),
+ *     30+t tower_t[3] [B,tower_hidden] (:586);
+ *   ItemImageExpert: 0 dropout [B,d] (model.py:384). */
+int mmoe_site_keys(uint64_t seed, uint32_t site, uint32_t* key0, uint32_t* key1);
 
 /* LayerNorm over the last dim (eps 1e-5, biased variance — nn.LayerNorm).
  * x: fp32 or T ([rows, d]); y: T and/or fp32 copies (either may be NULL); stats: fp32 [rows,2]

@@ -81,7 +81,10 @@ PROTOTYPES = {
     "mmoe_gemm_timing": (C.c_int, [C.c_int]),
     "mmoe_gemm_timing_read": (C.c_int, [_P(C.c_double), _P(C.c_double), _P(_i64), C.c_int]),
     "mmoe_set_sm_reserve": (C.c_int, [C.c_int]),
+    "mmoe_launch_trace": (C.c_int, [C.c_int]),
+    "mmoe_launch_trace_read": (C.c_int, [_P(_i32), C.c_int]),
     "mmoe_dropout_mask": (C.c_int, [_u32, _u32, _f, _i64, _vp, _vp]),
+    "mmoe_site_keys": (C.c_int, [C.c_uint64, _u32, _P(_u32), _P(_u32)]),
     "mmoe_layernorm_fwd": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _i64, _i32, C.c_int, _vp]),
     "mmoe_attention_fwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32,
                                      _f, _u32, _u32, C.c_int, _vp]),

@@ -996,6 +996,11 @@ static int fill_epi(EpiDev* d, const mmoe_gemm_problem& pr, int dtype) {
 }
 
 extern std::atomic<int> g_sm_reserve;
+// launch trace (tests): which instantiation each tensor-core launch used
+struct TraceEntry { int bn, ctas, rich, tiles; };
+static std::mutex g_trace_mu;
+static std::vector<TraceEntry> g_trace;
+static std::atomic<int> g_trace_on{0};
 static int launch_tc(const mmoe_gemm_problem* pr_in, int n, int dtype, cudaStream_t stream) {
   // k_splits == 0 on an accumulating problem means "choose": resolved below once the tile shape of the launch is known
   mmoe_gemm_problem pr[kMaxGroups];
@@ -1166,6 +1171,10 @@ static int launch_tc(const mmoe_gemm_problem* pr_in, int n, int dtype, cudaStrea
     kernels[bn == 64 ? 0 : (bn == 128 ? 1 : 2)][rich ? 1 : 0]<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(P);
   }
   MMOE_LAUNCH_OK("gemm_tc_kernel");
+  if (g_trace_on.load(std::memory_order_relaxed)) {
+    std::lock_guard<std::mutex> lk(g_trace_mu);
+    g_trace.push_back(TraceEntry{bn, ctas, rich ? 1 : 0, tiles});
+  }
   return 0;
 }
 
@@ -1318,6 +1327,25 @@ extern "C" int mmoe_gemm_timing_read(double* total_ms, double* total_flops, int6
   g_timed.clear();
   *total_ms = ms; *total_flops = fl; *launches = n;
   return 0;
+}
+
+// Launch trace of the tensor-core GEMM (tests: proves which kernel variant a shape resolved to).  enable != 0 clears and
+// starts recording; _read copies up to `max_entries` records of 4 ints {tile width, CTAs per tile, rich epilogue, tiles}
+// and returns the number recorded so far.
+extern "C" int mmoe_launch_trace(int enable) {
+  std::lock_guard<std::mutex> lk(mmoe::g_trace_mu);
+  mmoe::g_trace.clear();
+  mmoe::g_trace_on.store(enable ? 1 : 0);
+  return 0;
+}
+extern "C" int mmoe_launch_trace_read(int32_t* out, int max_entries) {
+  std::lock_guard<std::mutex> lk(mmoe::g_trace_mu);
+  const int n = (int)mmoe::g_trace.size();
+  for (int i = 0; i < n && i < max_entries && out != nullptr; ++i) {
+    out[4 * i] = mmoe::g_trace[i].bn; out[4 * i + 1] = mmoe::g_trace[i].ctas;
+    out[4 * i + 2] = mmoe::g_trace[i].rich; out[4 * i + 3] = mmoe::g_trace[i].tiles;
+  }
+  return n;
 }
 
 // SMs the persistent GEMM leaves free for concurrently running communication kernels (default 0, or env MMOE_SM_RESERVE).

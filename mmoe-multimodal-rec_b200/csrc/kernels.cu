@@ -505,6 +505,11 @@ extern "C" int mmoe_cast_f32(const float* x, void* y, int64_t n, int dtype, void
 extern "C" int mmoe_dropout_mask(uint32_t key0, uint32_t key1, float p, int64_t n, uint8_t* out, void* stream) {
   return dropout_mask(key0, key1, p, n, out, (cudaStream_t)stream);
 }
+extern "C" int mmoe_site_keys(uint64_t seed, uint32_t site, uint32_t* key0, uint32_t* key1) {
+  MMOE_CHECK(key0 != nullptr && key1 != nullptr, "site_keys: null output");
+  mmoe::site_keys(seed, site, key0, key1);
+  return 0;
+}
 extern "C" int mmoe_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, void* y_t, float* y_f32,
                                   float* stats, int64_t rows, int32_t d, int dtype, void* stream) {
   return layernorm_fwd(x, x_dtype, gamma, beta, y_t, y_f32, stats, rows, d, dtype, (cudaStream_t)stream);

@@ -78,14 +78,14 @@ class Case:
         return [True]
 
     # ---- oracle forward -------------------------------------------------
-    def oracle_forward(self, sd, inputs, relu_masks=None, trace=None) -> Tuple[torch.Tensor, ...]:
+    def oracle_forward(self, sd, inputs, relu_masks=None, trace=None, drop=None) -> Tuple[torch.Tensor, ...]:
         k = self.kind
-        kw = dict(relu_masks=relu_masks, trace=trace)
+        kw = dict(relu_masks=relu_masks, trace=trace, drop=drop)
         if k == "head":
-            return tuple(O.two_task_mmoe(sd, *inputs))
+            return tuple(O.two_task_mmoe(sd, *inputs, drop=drop))
         if k == "home_head":
             return tuple(O.home_mmoe(sd, *inputs, n_shared=self.ctor.get("n_shared_experts", 4),
-                                     n_task=self.ctor.get("n_task_experts", 2)))
+                                     n_task=self.ctor.get("n_task_experts", 2), drop=drop))
         if k == "cross":
             return (O.cross_expert(sd, *inputs, **kw),)
         if k == "cross_home":
@@ -95,7 +95,7 @@ class Case:
         if k == "fuse_home":
             return (O.cross_fuse(sd, *inputs, home=True, **kw),)
         if k == "img_pool":
-            return (O.item_image_pool(sd, *inputs, pool_type=self.ctor.get("pool_type", "mean")),)
+            return (O.item_image_pool(sd, *inputs, pool_type=self.ctor.get("pool_type", "mean"), drop=drop),)
         if k == "img_proj":
             return (O.image_projection(sd, *inputs)[1],)
         raise KeyError(k)
@@ -115,19 +115,26 @@ class Case:
         return keys
 
 
-def run_oracle(case: Case, dtype=torch.float64, relu_masks=None, trace=None):
-    """Forward + backward of the oracle.  Returns (outs, input_grads, param_grads).
-    ``relu_masks`` / ``trace``: see mmoe_oracle.encoder_layer (activation-pattern injection for low-precision parity)."""
-    sd = OrderedDict((k, v.to(dtype).clone().requires_grad_(True)) for k, v in case.state_dict().items())
+def run_oracle(case: Case, dtype=torch.float64, relu_masks=None, trace=None, device="cpu", drop=None):
+    """Forward + backward of the oracle.  Returns (outs, input_grads, param_grads) on the CPU.
+    ``relu_masks`` / ``trace``: see mmoe_oracle.encoder_layer (activation-pattern injection for low-precision parity).
+    ``device``: where the oracle's arithmetic runs — "cuda" lets the GPU tests use benchmark-sized batches (the oracle is
+    plain torch, float64 there as here).  ``drop``: keep-mask injection hook (mmoe_oracle._drop) for train-mode parity."""
+    sd = OrderedDict((k, v.to(device=device, dtype=dtype).clone().requires_grad_(True)) for k, v in case.state_dict().items())
     raw = case.inputs()
     meta = case.inputs_meta()
-    ins = [t.to(dtype).clone().requires_grad_(True) if f else t for t, f in zip(raw, meta)]
-    outs = case.oracle_forward(sd, ins, relu_masks, trace)
+    ins = [t.to(device=device, dtype=dtype).clone().requires_grad_(True) if f else t.to(device) for t, f in zip(raw, meta)]
+    if relu_masks is not None:
+        relu_masks = {k: v.to(device) for k, v in relu_masks.items()}
+    outs = case.oracle_forward(sd, ins, relu_masks, trace, drop=drop)
     cots = case.cotangents(outs)
-    torch.autograd.backward(list(outs), [c.to(dtype) for c in cots])
-    gin = [t.grad if f else None for t, f in zip(ins, meta)]
-    gp = OrderedDict((k, sd[k].grad) for k in sd)
-    return [o.detach() for o in outs], gin, gp
+    torch.autograd.backward(list(outs), [c.to(device=device, dtype=dtype) for c in cots])
+    gin = [t.grad.cpu() if f else None for t, f in zip(ins, meta)]
+    gp = OrderedDict((k, sd[k].grad.cpu() if sd[k].grad is not None else None) for k in sd)
+    if trace is not None:
+        for k in list(trace):
+            trace[k] = trace[k].cpu()
+    return [o.detach().cpu() for o in outs], gin, gp
 
 
 CASES: List[Case] = [

@@ -98,7 +98,7 @@ def multi_head_attention(sd: Mapping[str, Tensor], prefix: str, q_in: Tensor, kv
     v = v.reshape(B, Lk, n_head, hd).transpose(1, 2)
     scores = (q * (hd ** -0.5)) @ k.transpose(-1, -2)            # [B,H,Lq,Lk]
     if key_padding_mask is not None:
-        neg = torch.zeros(key_padding_mask.shape, dtype=scores.dtype)
+        neg = torch.zeros(key_padding_mask.shape, dtype=scores.dtype, device=scores.device)
         neg = neg.masked_fill(key_padding_mask, float("-inf"))
         scores = scores + neg[:, None, None, :]
     p = softmax_lastdim(scores)

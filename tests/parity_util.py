@@ -33,6 +33,10 @@ class FakeBackbone(torch.nn.Module):
         return _Tokens(pixel_values)
 
 
+def case_kwargs(case: C.Case):
+    return dict(case.ctor)
+
+
 def build_module(case: C.Case, device="cuda"):
     import mmoe_multimodal_rec_b200 as pkg
     M, H = pkg.modules, pkg.modules_home
@@ -65,13 +69,17 @@ def autocast_ctx(mode: str):
     return torch.autocast("cuda", dtype=torch.bfloat16 if mode == "bf16" else torch.float16)
 
 
-def run_cuda(case: C.Case, mode: str = "fp32", module=None):
-    """Forward + backward of the CUDA drop-in. Returns (outs, input_grads, param_grads) on CPU (fp32)."""
+def run_cuda(case: C.Case, mode: str = "fp32", module=None, seed=None):
+    """Forward + backward of the CUDA drop-in. Returns (outs, input_grads, param_grads) on CPU (fp32).
+    seed: torch.manual_seed right before the forward call (train mode: the call seed of the dropout masks is the next
+    draw from torch's CPU generator, see functional._new_seed)."""
     mod = module if module is not None else build_module(case)
     mod.zero_grad(set_to_none=True)
     raw = case.inputs()
     meta = case.inputs_meta()
     ins = [t.cuda().clone().requires_grad_(True) if f else t.cuda() for t, f in zip(raw, meta)]
+    if seed is not None:
+        torch.manual_seed(seed)
     with autocast_ctx(mode):
         if case.kind == "img_pool":
             out = mod(ins[0], trainable=True)
@@ -121,31 +129,88 @@ def cuda_relu_masks(entries) -> Dict[str, torch.Tensor]:
     return masks
 
 
-def per_sample_abs_scale(case: C.Case, keys: List[str], relu_masks=None) -> Dict[str, float]:
+def per_sample_abs_scale(case: C.Case, keys: List[str], relu_masks=None, device="cpu", drop=None) -> Dict[str, float]:
     """sum_b |dL_b/dp| for the given (tiny) parameters: the magnitude of the terms a batch-summed gradient is made of.
     A scalar gradient that is the sum of B cancelling per-sample terms can only be expected to be accurate relative
-    to that magnitude, not relative to its own (possibly much smaller) value."""
+    to that magnitude, not relative to its own (possibly much smaller) value.  Samples are independent in every module
+    of the path, so back-propagating the cotangent of one sample at a time through the full-batch graph gives dL_b/dp."""
     raw = case.inputs()
     meta = case.inputs_meta()
-    sd0 = case.state_dict()
-    full_out = case.oracle_forward({k: v.double() for k, v in sd0.items()}, [t.double() if f else t for t, f in zip(raw, meta)], relu_masks)
-    cots = case.cotangents(full_out)
+    sd = OrderedDict((k, v.to(device=device, dtype=torch.float64).clone().requires_grad_(True)) for k, v in case.state_dict().items())
+    ins = [t.to(device=device, dtype=torch.float64) if f else t.to(device) for t, f in zip(raw, meta)]
+    if relu_masks is not None:
+        relu_masks = {k: v.to(device) for k, v in relu_masks.items()}
+    outs = case.oracle_forward(sd, ins, relu_masks, None, drop=drop)
+    cots = [c.to(device=device, dtype=torch.float64) for c in case.cotangents([o.detach().cpu() for o in outs])]
     acc = {k: 0.0 for k in keys}
-    rows_per_sample = {"cross": 64, "cross_home": 64, "fuse": 2, "fuse_home": 2}.get(case.kind, 1)
     for b in range(case.B):
-        sd = OrderedDict((k, v.double().clone().requires_grad_(True)) for k, v in sd0.items())
-        ins = [t[b:b + 1].double() if f else t[b:b + 1] for t, f in zip(raw, meta)]
-        m = None
-        if relu_masks is not None:
-            m = {k: v.reshape(case.B, rows_per_sample, -1)[b] for k, v in relu_masks.items()}
-        outs = case.oracle_forward(sd, ins, m)
-        torch.autograd.backward(list(outs), [c[b:b + 1].double() for c in cots])
-        for k in keys:
-            acc[k] += float(sd[k].grad.abs().max())
+        sel = []
+        for c in cots:
+            m = torch.zeros_like(c)
+            m[b] = c[b]
+            sel.append(m)
+        gs = torch.autograd.grad(list(outs), [sd[k] for k in keys], sel, retain_graph=True)
+        for k, g in zip(keys, gs):
+            acc[k] += float(g.abs().max())
     return acc
 
 
-def compare_with_oracle(case: C.Case, mode: str, module=None, stats: Optional[dict] = None) -> Dict[str, float]:
+def call_seed(seed: int) -> int:
+    """The mmoe_call.seed a module forward draws after torch.manual_seed(seed) (functional._new_seed)."""
+    torch.manual_seed(seed)
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+_ENC_SITES = {"self_attn.probs": 0, "dropout1": 1, "dropout": 2, "dropout2": 3}
+
+
+def site_id(case: C.Case, name: str) -> int:
+    """Dropout site number (include/mmoe_b200.h, mmoe_site_keys) of one of the oracle's dropout call sites."""
+    import re
+    m = re.match(r"(self_user|self_item|layers)\.(\d+)\.(self_attn\.probs|dropout1|dropout2|dropout)$", name)
+    if m:
+        return 16 * int(m.group(2)) + (8 if m.group(1) == "self_item" else 0) + _ENC_SITES[m.group(3)]
+    k = case.kind
+    if k in ("cross", "cross_home"):
+        return {"cross_attn.probs": 100, "pool.weights": 101, "mlp.2": 102, "mlp.4": 103}[name]
+    if k in ("fuse", "fuse_home"):
+        return {"proj.3": 100}[name]
+    if k == "head":
+        return {"tower_good.3": 10, "tower_best.3": 11, "tower_good.6": 20, "tower_best.6": 21}[name]
+    if k == "home_head":
+        ns, nt = case.ctor.get("n_shared_experts", 4), case.ctor.get("n_task_experts", 2)
+        m = re.match(r"(meta_experts|task_experts_good|task_experts_best)\.(\d+)\.2$", name)
+        if m:
+            return 10 + {"meta_experts": 0, "task_experts_good": ns, "task_experts_best": ns + nt}[m.group(1)] + int(m.group(2))
+        return {"tower_good.3": 30, "tower_best.3": 31}[name]
+    if k == "img_pool":
+        return {"dropout": 0}[name]
+    raise KeyError((k, name))
+
+
+def make_drop_hook(case: C.Case, seed: int, p: float, used: Optional[list] = None):
+    """drop(site, tensor) for the oracle: applies the keep-mask the CUDA kernels use for that site (keyed counter hash of
+    the flat element index, exported by the library as mmoe_site_keys + mmoe_dropout_mask) and the 1/(1-p) scale."""
+    import ctypes as Ct
+    import mmoe_multimodal_rec_b200 as pkg
+    L = pkg.lib()
+
+    def drop(site, x):
+        if p <= 0.0:
+            return x
+        k0, k1 = Ct.c_uint32(), Ct.c_uint32()
+        assert L.mmoe_site_keys(seed, site_id(case, site), Ct.byref(k0), Ct.byref(k1)) == 0
+        keep = torch.empty(x.numel(), dtype=torch.uint8, device="cuda")
+        assert L.mmoe_dropout_mask(k0.value, k1.value, p, x.numel(), keep.data_ptr(), torch.cuda.current_stream().cuda_stream) == 0
+        if used is not None:
+            used.append((site, float(keep.float().mean()), x.numel()))
+        keep = keep.view(x.shape).to(device=x.device, dtype=x.dtype)
+        return x * keep * (1.0 / (1.0 - p))
+    return drop
+
+
+def compare_with_oracle(case: C.Case, mode: str, module=None, stats: Optional[dict] = None, device="cpu",
+                        train_seed: Optional[int] = None, drop_p: float = 0.1) -> Dict[str, float]:
     """Normalised errors of every output / gradient of the CUDA path against the float64 oracle.
 
     16-bit modes, modules with ReLU feed-forward layers: rounding the GEMM operands to 16 bits flips the sign of
@@ -161,28 +226,38 @@ def compare_with_oracle(case: C.Case, mode: str, module=None, stats: Optional[di
     inject = mode != "fp32" and case.kind in ("cross", "cross_home", "fuse", "fuse_home")
     if inject:
         Fn.DEBUG_SAVED = []
+    drop = None
+    if train_seed is not None:
+        # train mode: the module (in .train()) draws its call seed right after torch.manual_seed(train_seed); the oracle gets
+        # the very same keep-masks through its `drop=` hook
+        sites = []
+        drop = make_drop_hook(case, call_seed(train_seed), drop_p, sites)
+        if stats is not None:
+            stats["drop_sites"] = sites
     try:
-        c_out, c_gin, c_gp = run_cuda(case, mode, module)
+        c_out, c_gin, c_gp = run_cuda(case, mode, module, seed=train_seed)
         entries = Fn.DEBUG_SAVED
     finally:
         Fn.DEBUG_SAVED = None
     if inject:
         masks = cuda_relu_masks(entries)
         trace: Dict[str, torch.Tensor] = {}
-        o_out, o_gin, o_gp = C.run_oracle(case, torch.float64, relu_masks=masks, trace=trace)
+        # (train mode: h != 0 means "ReLU active and kept"; the oracle multiplies by the keep-mask as well, which is idempotent)
+        o_out, o_gin, o_gp = C.run_oracle(case, torch.float64, relu_masks=masks, trace=trace, device=device, drop=drop)
         flips, total, worst = 0, 0, 0.0
-        for key, m in masks.items():
-            z = trace[key.replace(".relu", ".ffn_pre")].reshape(m.shape)
-            diff = (z > 0) != m
-            flips += int(diff.sum())
-            total += m.numel()
-            if diff.any():
-                worst = max(worst, float(z[diff].abs().max() / z.std()))
+        if drop is None:
+            for key, m in masks.items():
+                z = trace[key.replace(".relu", ".ffn_pre")].reshape(m.shape)
+                diff = (z > 0) != m
+                flips += int(diff.sum())
+                total += m.numel()
+                if diff.any():
+                    worst = max(worst, float(z[diff].abs().max() / z.std()))
         if stats is not None:
             stats["flip_frac"] = flips / max(total, 1)
             stats["flip_max_rel_z"] = worst
     else:
-        o_out, o_gin, o_gp = C.run_oracle(case, torch.float64)
+        o_out, o_gin, o_gp = C.run_oracle(case, torch.float64, device=device, drop=drop)
     errs: Dict[str, float] = {}
     for j, (a, b) in enumerate(zip(c_out, o_out)):
         errs[f"out{j}"] = nerr(a, b)
@@ -199,7 +274,7 @@ def compare_with_oracle(case: C.Case, mode: str, module=None, stats: Optional[di
     # value are re-judged relative to the magnitude of their per-sample terms (cancellation-aware)
     tiny = [k for k, ref in o_gp.items() if k in used and ref.numel() <= 8 and errs["d_" + k] > TOL[mode] and c_gp.get(k) is not None]
     if tiny and case.B > 1:
-        scale = per_sample_abs_scale(case, tiny, masks if inject else None)
+        scale = per_sample_abs_scale(case, tiny, masks if inject else None, device=device, drop=drop)
         for k in tiny:
             errs["d_" + k] = float((c_gp[k].double() - o_gp[k].double()).abs().max()) / max(scale[k], 1e-30)
     return errs

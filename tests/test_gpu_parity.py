@@ -38,6 +38,53 @@ def test_16bit_autocast_matches_oracle(case, mode):
         assert stats["flip_frac"] < 0.01 and stats["flip_max_rel_z"] < 0.05, stats
 
 
+# Benchmark-sized batches: at B = 128 (README config, 8192 sentence rows) and B = 512 (train.py default,
+# the batch bench.py times) the GEMM launcher resolves to the CTA-pair 256x256 kernel with the bit-mask FFN epilogues — the
+# kernels the benchmark actually runs.  The float64 oracle runs on the GPU here (plain torch, same code as on the CPU).
+BIG_CASES = [
+    C.Case("cross_b128", "cross", 128, 131), C.Case("cross_home_b128", "cross_home", 128, 132),
+    C.Case("fuse_b128", "fuse", 128, 141), C.Case("fuse_home_b128", "fuse_home", 128, 142),
+    C.Case("home_head_b512", "home_head", 512, 121, dict(tower_hidden=512)),
+    C.Case("head_b4096", "head", 4096, 112),
+]
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "fp16"])
+@pytest.mark.parametrize("case", BIG_CASES, ids=[c.name for c in BIG_CASES])
+def test_benchmark_sized_batches_match_oracle(case, mode):
+    import mmoe_multimodal_rec_b200 as pkg
+    L = pkg.lib()
+    L.mmoe_launch_trace(1)
+    stats = {}
+    errs = PU.compare_with_oracle(case, mode, stats=stats, device="cuda")
+    n = L.mmoe_launch_trace_read(None, 0)
+    L.mmoe_launch_trace(0)
+    _assert_ok(errs, PU.TOL[mode], f"{case.name} {mode}")
+    if stats:
+        assert stats["flip_frac"] < 0.01 and stats["flip_max_rel_z"] < 0.05, stats
+    if mode != "fp32":
+        assert n > 0           # the tensor-core engine ran
+
+
+def test_cross_expert_at_the_benchmark_batch_uses_the_pair_kernel_and_matches():
+    """B = 512 under bf16 autocast: exactly bench.py's cross-expert call (eval arithmetic), M = 32768 rows."""
+    import ctypes as Ct
+    import mmoe_multimodal_rec_b200 as pkg
+    L = pkg.lib()
+    case = C.Case("cross_b512", "cross", 512, 231)
+    L.mmoe_launch_trace(1)
+    stats = {}
+    errs = PU.compare_with_oracle(case, "bf16", stats=stats, device="cuda")
+    n = L.mmoe_launch_trace_read(None, 0)
+    buf = (Ct.c_int32 * (4 * n))()
+    L.mmoe_launch_trace_read(buf, n)
+    L.mmoe_launch_trace(0)
+    pair = sum(1 for i in range(n) if buf[4 * i + 1] == 2)
+    assert pair >= 40, f"only {pair} of {n} GEMM launches used the CTA-pair kernel"
+    _assert_ok(errs, PU.TOL["bf16"], "cross_b512 bf16")
+    assert stats["flip_frac"] < 0.01 and stats["flip_max_rel_z"] < 0.05, stats
+
+
 def test_16bit_forward_matches_fp64_oracle_without_any_injection():
     """Forward outputs have no discontinuity: compare straight against the fp64 oracle."""
     for name in ("cross_b3", "fuse_b8", "cross_home_b3", "fuse_home_b8"):
