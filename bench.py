@@ -12,10 +12,18 @@ stack -> TwoTaskMMoE -> 2x BCEWithLogits -> backward.  Modules are in train() mo
 training).  Synthetic inputs of the shapes the encoders produce (sentence vectors [B,64,768] + masks, doc
 vectors, ViT tokens [B,197,768]) and random-init weights; the text encoders / ViT backbone are the reference's
 own torch modules and are not part of the timed path (north_star: "timed separately").
-For N > 1 each rank runs the same per-GPU batch (weak scaling) and the gradients are averaged over NCCL, overlapped with
-backward: by the package's native flat-buffer exchange (default) or by DistributedDataParallel wrappers (--ddp).
+
+N > 1 (weak scaling, fixed per-GPU batch): the headline is measured the way the reference's train.py runs the modules
+— one DistributedDataParallel wrapper per module with default arguments (train.py:136-139), the head called through
+`.module` (train.py:251) — so the number is what the UNCHANGED script gets from the drop-ins.  The package's own
+flat-buffer gradient exchange (functional.enable_grad_allreduce) is timed next to it and reported under
+`native_exchange`.
+
 The headline pass carries no per-launch events; the GEMM roofline is measured in a second, single-stream pass of the
-same steps with a CUDA event pair around every GEMM launch.
+same steps with a CUDA event pair around every GEMM launch.  At N = 1 the line also carries: `eager_b200` (the same
+step in eager PyTorch — torch's own cuBLASLt/SDPA kernels — on the same GPU and weights), `cpu_baseline` (the same
+step on the host cores), and `extra` (TwoTaskMMoE alone against the HBM roofline, the HoME path, the forward-only
+scoring sweep: BASELINE configs[0], [3], [4]).
 
 One JSON line on stdout (rank 0); see README / DESIGN.md for the keys.
 """
@@ -26,7 +34,6 @@ import ctypes as C
 import gc
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -41,6 +48,9 @@ UNIT = "samples/s"
 S, D, NTOK = 64, 768, 197
 # algorithmic GEMM FLOPs of the v1 fusion path per sample, fwd+bwd (SURVEY.md §8d / BASELINE.md §3)
 FLOP_PER_SAMPLE = 12.366e9
+FLOP_PER_SAMPLE_HOME = 12.469e9
+HEAD_BYTES_PER_SAMPLE = 55328.0          # TwoTaskMMoE fwd+bwd, fp32 I/O
+POS_W_GOOD, POS_W_BEST = 858627.0 / 990303.0, 1328721.0 / 520209.0      # train.py:189-192
 
 
 def log(*a):
@@ -50,18 +60,22 @@ def log(*a):
 # ----------------------------------------------------------------------------------------------
 # synthetic inputs (oracle/synth.py is test infrastructure; the bench makes its own with torch RNG)
 # ----------------------------------------------------------------------------------------------
-def make_host_batch(B: int, seed: int, pin: bool):
+def make_host_batch(B: int, seed: int, pin: bool, lowp_stream: bool = False):
+    """lowp_stream: the three big activation tensors as bf16 on the host (the end-to-end leg ships them in 16 bits; the
+    modules cast on the device — under autocast their first use is a 16-bit GEMM operand anyway)."""
     g = torch.Generator().manual_seed(seed)
-    def t(*shape):
+    def t(*shape, lowp=False):
         x = torch.randn(*shape, generator=g)
+        if lowp:
+            x = x.to(torch.bfloat16)
         return x.pin_memory() if pin else x
     lens_u = torch.randint(1, S + 1, (B,), generator=g)
     lens_i = torch.randint(1, S + 1, (B,), generator=g)
     ar = torch.arange(S)[None]
     batch = {
-        "u_sent": t(B, S, D), "i_sent": t(B, S, D),
+        "u_sent": t(B, S, D, lowp=lowp_stream), "i_sent": t(B, S, D, lowp=lowp_stream),
         "u_mask": (ar >= lens_u[:, None]), "i_mask": (ar >= lens_i[:, None]),
-        "u_doc": t(B, D), "i_doc": t(B, D), "img_tokens": t(B, NTOK, D),
+        "u_doc": t(B, D), "i_doc": t(B, D), "img_tokens": t(B, NTOK, D, lowp=lowp_stream),
         "y_good": (torch.rand(B, generator=g) < 0.5).float(), "y_best": (torch.rand(B, generator=g) < 0.5).float(),
     }
     if pin:
@@ -89,7 +103,7 @@ class Passthrough(torch.nn.Module):
 
 
 # ----------------------------------------------------------------------------------------------
-# clocks sampler (nvidia-smi during the timed region)
+# clocks sampler (NVML during the timed region)
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region through NVML (in-process thread, 20 ms period;
@@ -104,10 +118,8 @@ class ClockSampler:
         try:
             import pynvml
             pynvml.nvmlInit()
-            # CUDA_VISIBLE_DEVICES may remap indices: resolve through the PCI bus id of the torch device
-            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
             self._nv = pynvml
-            self._h = pynvml.nvmlDeviceGetHandleByIndex(index) if bus is None else pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
         except Exception:
             self._h = None
 
@@ -148,64 +160,75 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port of the reference's modules on the host cores
+# the reference's composition on stock torch modules (oracle/eager_ref.py): CPU arm and eager-on-B200 arm
 # ----------------------------------------------------------------------------------------------
-def cpu_oracle_step_fn(B: int):
-    """fwd+bwd of the same path through oracle/ (CPU restatement of the reference) in fp32, eval-mode arithmetic
-    (the oracle has no RNG; dropout costs the reference extra time on CPU, so this favours the baseline)."""
-    from oracle import mmoe_oracle as O
-    from oracle import synth
-    torch.manual_seed(0)
-    sds = {
-        "img": synth.fill_state_dict(synth.image_wrapper_shapes(), 1),
-        "cross": synth.fill_state_dict(synth.cross_expert_shapes(), 2),
-        "concat_ui": synth.fill_state_dict(synth.cross_fuse_shapes(), 3),
-        "concat_ti": synth.fill_state_dict(synth.cross_fuse_shapes(), 4),
-        "head": synth.fill_state_dict(synth.mmoe_head_shapes(), 5),
-    }
-    for sd in sds.values():
-        for v in sd.values():
-            v.requires_grad_(True)
-    b = make_host_batch(B, 99, pin=False)
-    for k in ("u_sent", "i_sent", "u_doc", "i_doc"):
-        b[k].requires_grad_(True)
+def build_modules(dev, train=True, seed=1234):
+    import mmoe_multimodal_rec_b200 as pkg
+    M = pkg.modules
+    torch.manual_seed(seed)
+    mods = {"img": M.ItemImageExpert(Passthrough(), pool_type="mean"), "cross": M.RobustTextCrossExpert(),
+            "concat_ui": M.EnhancedCrossFuse(), "concat_ti": M.EnhancedCrossFuse(), "head": M.TwoTaskMMoE()}
+    for m in mods.values():
+        m.to(dev).train(train)
+    return mods
+
+
+def eager_step_fn(mods, b, dev, autocast_dtype):
+    """fwd+bwd of the same micro-step in eager PyTorch: the modules' own nn.TransformerEncoderLayer / nn.MultiheadAttention /
+    nn.Linear containers CALLED the way the reference's forward bodies call them (oracle/eager_ref.py), train mode."""
+    from oracle import eager_ref as E
+    pw_g, pw_b = torch.tensor(POS_W_GOOD, device=dev), torch.tensor(POS_W_BEST, device=dev)
+    grad_keys = ("u_sent", "i_sent", "u_doc", "i_doc")
 
     def step():
-        for sd in sds.values():
-            for v in sd.values():
-                v.grad = None
-        lg, lb = O.v1_fusion_path(sds, b["u_sent"], b["u_mask"], b["i_sent"], b["i_mask"], b["u_doc"], b["i_doc"], b["img_tokens"])
-        loss = O.bce_with_logits(lg, b["y_good"], O.POS_WEIGHT_GOOD) + O.bce_with_logits(lb, b["y_best"], O.POS_WEIGHT_BEST)
+        for m in mods.values():
+            m.zero_grad(set_to_none=True)
+        ins = {k: (v.detach().requires_grad_(True) if k in grad_keys else v) for k, v in b.items()}
+        loss = E.v1_fusion_step(mods, ins, pw_g, pw_b, autocast_dtype)
         loss.backward()
-        return float(loss.detach())
+        return loss
     return step
 
 
-def time_cpu_oracle(B: int, steps: int, warmup: int):
+def time_cpu_reference(B: int, steps: int, warmup: int, budget_s: float):
+    """The reference's CPU path for this workload: its forward composition on stock torch modules (fp32, train mode,
+    torch's own dropout), all host threads, B samples per step.  Timed steps are cut short when `budget_s` runs out."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step = cpu_oracle_step_fn(B)
+    dev = torch.device("cpu")
+    from oracle import eager_ref as E
+    mods = E.make_v1_modules(dev, train=True)            # stock torch.nn containers only: nothing of the package on this arm
+    b = make_host_batch(B, 99, pin=False)
+    step = eager_step_fn(mods, b, dev, None)
+    t_begin = time.perf_counter()
     for _ in range(warmup):
         step()
+        if time.perf_counter() - t_begin > budget_s / 3:
+            break
+    done = 0
     t0 = time.perf_counter()
-    for _ in range(steps):
+    while done < steps:
         step()
-    dt = (time.perf_counter() - t0) / steps
-    return B / dt, dt * 1e3, cores
+        done += 1
+        if time.perf_counter() - t_begin > budget_s and done >= 1:
+            break
+    dt = (time.perf_counter() - t0) / done
+    return B / dt, dt * 1e3, cores, done
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     B = args.ref_batch
-    value, ms, cores = time_cpu_oracle(B, max(args.steps, 1), max(args.warmup, 1))
+    value, ms, cores, done = time_cpu_reference(B, max(args.steps, 1), max(min(args.warmup, 2), 1), args.ref_budget_s)
+    sample = (f"reference forward composition on stock torch.nn modules (oracle/eager_ref.py), fp32, train mode, {B}-sample batch per step, "
+              f"fwd+bwd, {done} timed steps of the {args.steps} requested ({ms:.0f} ms/step; bounded to ~{args.ref_budget_s:.0f} s)")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.batch, args.gpus) | {"sample": f"{B} samples per step on the host CPU"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"oracle/ port of the reference modules, fp32, {B}-sample batch, fwd+bwd, {args.steps} steps"},
+        "config": workload_config(args.batch, args.gpus) | {"sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -222,6 +245,95 @@ def workload_config(B, n_gpus):
 
 
 # ----------------------------------------------------------------------------------------------
+def cuda_time(fn, warm, reps):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def extra_measurements(dev, hbm_gbs, peak_tf):
+    """BASELINE configs[0] (head alone, HBM roofline), [3] (HoME path, one GPU) and [4] (forward-only scoring sweep)."""
+    import torch.nn.functional as F
+    import mmoe_multimodal_rec_b200 as pkg
+    M, H = pkg.modules, pkg.modules_home
+    out = {}
+    # ---- TwoTaskMMoE alone, fwd+bwd: bandwidth-bound; 55,328 algorithmic bytes per sample (read expert_vecs twice, write its grad)
+    head = M.TwoTaskMMoE().to(dev).train()
+    rows = []
+    for mode, B in (("bf16", 65536), ("bf16", 256), ("fp32", 65536), ("fp32", 256)):
+        ev = torch.randn(B, 6, D, device=dev, requires_grad=True)
+
+        def step():
+            head.zero_grad(set_to_none=True)
+            ev.grad = None
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16")):
+                lg, lb = head(ev)
+            (lg.float().sum() + lb.float().sum()).backward()
+        ms = cuda_time(step, 3, 10)
+        gbs = HEAD_BYTES_PER_SAMPLE * B / (ms * 1e-3) / 1e9
+        rows.append({"mode": mode, "B": B, "ms": ms, "samples_per_s": B / ms * 1e3, "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / hbm_gbs})
+        del ev
+    out["head_only_fwd_bwd"] = {"bound": "hbm", "peak_GBps": hbm_gbs, "bytes_per_sample": HEAD_BYTES_PER_SAMPLE, "rows": rows}
+    # ---- HoME fusion path (cross' + 2 fuse' + image projection head + HOME_MMoE_Complete(768,4,2,512)), fwd+bwd bf16, B = 512
+    B = 512
+    cross, cui, cti = H.RobustTextCrossExpert().to(dev).train(), H.EnhancedCrossFuse().to(dev).train(), H.EnhancedCrossFuse().to(dev).train()
+    hhead = H.HOME_MMoE_Complete(expert_dim=D, n_shared_experts=4, n_task_experts=2, tower_hidden=512).to(dev).train()
+    img = H.ImageExpertWithProjection(Passthrough()).to(dev).train()
+    hm = [cross, cui, cti, hhead, img]
+    b = {k: v.to(dev) for k, v in make_host_batch(B, 5, pin=False).items()}
+    u, i, ud, idoc = (b[k].requires_grad_(True) for k in ("u_sent", "i_sent", "u_doc", "i_doc"))
+
+    def home_step():
+        for m in hm:
+            m.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            img_vec, proj = img(b["img_tokens"])
+            ui = cross(u, b["u_mask"], i, b["i_mask"])
+            xui, xti = cui(ud, img_vec), cti(idoc, img_vec)
+            ev = torch.stack([ud, idoc, img_vec.float(), ui, xui, xti], 1)      # (HomeExpertWrapper BN is script-side)
+            lg, lb = hhead(ev)
+            loss = F.binary_cross_entropy_with_logits(lg.float(), b["y_good"]) + F.binary_cross_entropy_with_logits(lb.float(), b["y_best"]) + \
+                0.01 * proj.float().pow(2).mean()
+        loss.backward()
+    ms = cuda_time(home_step, 3, 10)
+    tf = FLOP_PER_SAMPLE_HOME * B / (ms * 1e-3) / 1e12
+    out["home_path_fwd_bwd_bf16"] = {"B": B, "ms": ms, "samples_per_s": B / ms * 1e3, "path_tflops": tf, "path_frac_of_peak": tf / peak_tf,
+                                     "note": "single stream"}
+    del hm, cross, cui, cti, hhead, img
+    # ---- forward-only scoring (inference_and_auc.py:130-156), v1 path, no grad
+    mods = build_modules(dev, train=False)
+    rows = []
+    for Bs in (1024, 4096, 16384, 65536):
+        bb = {k: v.to(dev) for k, v in make_host_batch(min(Bs, 4096), 6, pin=False).items()}
+        if Bs > 4096:
+            bb = {k: v.repeat((Bs // 4096,) + (1,) * (v.dim() - 1)) for k, v in bb.items()}
+        for mode in ("bf16", "fp32"):
+            if mode == "fp32" and Bs > 16384:
+                continue
+
+            def score():
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16")):
+                    img_vec = mods["img"](bb["img_tokens"])
+                    ui = mods["cross"](bb["u_sent"], bb["u_mask"], bb["i_sent"], bb["i_mask"])
+                    ev = torch.stack([bb["u_doc"], bb["i_doc"], img_vec, ui, mods["concat_ui"](bb["u_doc"], img_vec),
+                                      mods["concat_ti"](bb["i_doc"], img_vec)], 1)
+                    lg, lb = mods["head"](ev)
+                return torch.sigmoid(lg), torch.sigmoid(lb)
+            ms = cuda_time(score, 1, 2 if mode == "fp32" else 4)
+            rows.append({"mode": mode, "B": Bs, "ms": ms, "samples_per_s": Bs / ms * 1e3, "path_tflops": 4.122e9 * Bs / (ms * 1e-3) / 1e12})
+        del bb
+    out["v1_forward_scoring"] = {"rows": rows}
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 _REAL_STDOUT = None
 
 
@@ -232,17 +344,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=512, help="per-GPU batch (train.py default 512)")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--ref-batch", type=int, default=16, help="samples per step of the CPU reference arm")
-    ap.add_argument("--cpu-baseline-batch", type=int, default=16)
+    ap.add_argument("--ref-batch", type=int, default=512, help="samples per step of the CPU reference arm")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="wall-clock bound of the CPU reference arm")
+    ap.add_argument("--cpu-baseline-batch", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip eager_b200 / extra configs (N = 1 only)")
     ap.add_argument("--eval-mode", action="store_true", help="dropout off (debug)")
     ap.add_argument("--no-side-stream", action="store_true", help="run both fuse experts on the main stream")
-    ap.add_argument("--bucket-mb", type=int, default=25, help="DDP gradient bucket size (with --ddp)")
-    ap.add_argument("--ddp", action="store_true", help="N > 1: wrap the modules in torch DistributedDataParallel (as train.py "
-                                                        "does) instead of the native flat-buffer gradient all-reduce")
+    ap.add_argument("--exchange", default="both", choices=["ddp", "native", "both"],
+                    help="N > 1: which gradient exchange to time; the headline is always the DDP wrappers when measured")
+    ap.add_argument("--ddp-view", action="store_true", help="gradient_as_bucket_view=True on the DDP wrappers (train.py passes nothing)")
     ap.add_argument("--nccl-ctas", type=int, default=0,
-                    help="N>1: if > 0, cap NCCL at this many CTAs and keep as many SMs free of GEMM CTAs (measured: capping "
-                         "lengthens the exposed part of the all-reduce at N=2; default leaves NCCL alone)")
+                    help="N>1: if > 0, cap NCCL at this many CTAs and keep as many SMs free of GEMM CTAs")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -270,8 +383,6 @@ def main():
         sys.stdout.flush()
         _REAL_STDOUT = os.fdopen(os.dup(1), "w")
         os.dup2(2, 1)
-        # ~280 MB of gradients per step overlap ~8 ms of backward: a few NCCL CTAs are plenty, and every SM NCCL holds
-        # is an SM the persistent GEMM cannot use while it runs
         if args.nccl_ctas > 0:
             os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_ctas))
         dist.init_process_group("nccl", device_id=dev)
@@ -280,36 +391,21 @@ def main():
     if distributed and args.nccl_ctas > 0:
         L.mmoe_set_sm_reserve(args.nccl_ctas)
 
-    M = pkg.modules
-    torch.manual_seed(1234)
-    img = M.ItemImageExpert(Passthrough(), pool_type="mean").to(dev)
-    cross = M.RobustTextCrossExpert().to(dev)
-    cui = M.EnhancedCrossFuse().to(dev)
-    cti = M.EnhancedCrossFuse().to(dev)
-    head = M.TwoTaskMMoE().to(dev)
+    mods_d = build_modules(dev, train=not args.eval_mode)
+    img, cross, cui, cti, head = (mods_d[k] for k in ("img", "cross", "concat_ui", "concat_ti", "head"))
     mods = [img, cross, cui, cti, head]
-    for m in mods:
-        m.train(not args.eval_mode)
-    cross_c, cui_c, cti_c, head_c = cross, cui, cti, head
-    if distributed and args.ddp:
-        # the reference scripts' way (train.py:133-139): one DistributedDataParallel wrapper per module
-        from torch.nn.parallel import DistributedDataParallel as DDP
-        cross_c, cui_c, cti_c, head_c = (DDP(m, device_ids=[local_rank], gradient_as_bucket_view=True, bucket_cap_mb=args.bucket_mb)
-                                         for m in (cross, cui, cti, head))
-    elif distributed:
-        # native exchange: every module backward all-reduces (averages) its ONE flat gradient buffer as soon as it is
-        # complete — no per-parameter hooks or bucket copies (DDP spends ~1 ms/step on ~300 per-parameter copy kernels)
+    if distributed:
         for m in mods:
             for prm in m.parameters():
                 dist.broadcast(prm.data, src=0)
-        pkg.functional.enable_grad_allreduce()
-    pw_g = torch.tensor(858627.0 / 990303.0, device=dev)      # train.py:189-192
-    pw_b = torch.tensor(1328721.0 / 520209.0, device=dev)
+    call = {"cross": cross, "cui": cui, "cti": cti, "head": head}
+    pw_g = torch.tensor(POS_W_GOOD, device=dev)
+    pw_b = torch.tensor(POS_W_BEST, device=dev)
 
     B = args.batch
     n_host = 2
-    host = [make_host_batch(B, 1234 + rank * 17 + j, pin=True) for j in range(n_host)]
-    resident = {k: v.to(dev) for k, v in host[0].items()}
+    host = [make_host_batch(B, 1234 + rank * 17 + j, pin=True, lowp_stream=True) for j in range(n_host)]
+    resident = {k: v.to(dev) for k, v in make_host_batch(B, 1234 + rank * 17, pin=False).items()}
     grad_keys = ("u_sent", "i_sent", "u_doc", "i_doc")
 
     side_stream = None if args.no_side_stream else torch.cuda.Stream(device=dev)
@@ -322,6 +418,7 @@ def main():
         for m in mods:
             m.zero_grad(set_to_none=True)
         ins = {k: (v.detach().requires_grad_(True) if k in grad_keys else v) for k, v in b.items()}
+        cross_c, cui_c, cti_c, head_c = call["cross"], call["cui"], call["cti"], call["head"]
         with torch.autocast("cuda", dtype=torch.bfloat16):
             img_vec = img(ins["img_tokens"], trainable=False)
             side = side_stream if use_side[0] else None
@@ -352,12 +449,11 @@ def main():
                 ui = cross_c(ins["u_sent"], ins["u_mask"], ins["i_sent"], ins["i_mask"])
                 xui = cui_c(ins["u_doc"], img_vec)
                 xti = cti_c(ins["i_doc"], img_vec)
-            ev = torch.stack([ins["u_doc"], ins["i_doc"], img_vec, ui, xui, xti], dim=1)
+            ev = torch.stack([ins["u_doc"].float(), ins["i_doc"].float(), img_vec, ui, xui, xti], dim=1)
             lg, lb = head_c(ev)
             loss = F.binary_cross_entropy_with_logits(lg.float(), ins["y_good"], pos_weight=pw_g) + \
                    F.binary_cross_entropy_with_logits(lb.float(), ins["y_best"], pos_weight=pw_b)
         loss.backward()
-        pkg.functional.wait_grad_allreduce()       # no-op unless the native gradient exchange is on
         return loss
 
     def barrier():
@@ -365,8 +461,68 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_loop(n_steps):
+        """n steps bracketed by barrier + synchronize; returns (total ms, sorted per-step ms, slowest index, host stats)."""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps + 1)]
+        for e in step_ev:
+            e.record()            # torch creates the CUDA event lazily at the first record: do that outside the timed loop
+        barrier()
+        ev0.record()
+        t_host = time.perf_counter()
+        step_ev[0].record()
+        host_t = [time.perf_counter()]
+        for i in range(n_steps):
+            if i >= 2 and not os.environ.get("BENCH_NO_THROTTLE"):
+                step_ev[i - 1].synchronize()   # stay at most two steps ahead of the device (bounded launch-queue depth)
+            step(resident)
+            step_ev[i + 1].record()
+            host_t.append(time.perf_counter())
+        host_ms = (time.perf_counter() - t_host) * 1e3 / n_steps      # time the host needs to ENQUEUE a step
+        ev1.record()
+        barrier()
+        per = [step_ev[i].elapsed_time(step_ev[i + 1]) for i in range(n_steps)]
+        slow = max(range(n_steps), key=lambda i: per[i])
+        per.sort()
+        return ev0.elapsed_time(ev1), per, slow, host_ms, max((host_t[i + 1] - host_t[i]) * 1e3 for i in range(n_steps))
+
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if distributed:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    W = max(args.warmup, 3)
+    native_result = None
+    # ---------------- N > 1: the package's own gradient exchange, timed first (before DDP hooks exist) ----------------
+    if distributed and args.exchange in ("native", "both"):
+        pkg.functional.enable_grad_allreduce()
+        for _ in range(W):
+            step(resident)
+        barrier()
+        ms_total, per_step, _, host_ms, _ = timed_loop(args.steps)
+        ms_native = max_over_ranks(ms_total) / args.steps
+        native_result = {"value": B * world / (ms_native * 1e-3), "unit": UNIT, "ms_per_step": ms_native,
+                         "host_enqueue_ms_per_step": host_ms,
+                         "how": "functional.enable_grad_allreduce(): one in-place NCCL all-reduce (AVG) per module / encoder-layer stage on the "
+                                "flat fp32 gradient buffer the backward kernels already wrote, started when the stage is enqueued, installed "
+                                "into .grad by an engine callback at the end of backward; no per-parameter hooks or bucket copies"}
+        pkg.functional.disable_grad_allreduce()
+    exchange = "none"
+    if distributed and args.exchange in ("ddp", "both"):
+        # the reference scripts' way (train.py:136-139): one DistributedDataParallel wrapper per module, default arguments;
+        # the head is called through .module (train.py:251), so its gradient is not exchanged
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        kw = {"gradient_as_bucket_view": True} if args.ddp_view else {}
+        wrapped = {k: DDP(m, device_ids=[local_rank], **kw) for k, m in (("cross", cross), ("cui", cui), ("cti", cti), ("head", head))}
+        call = {"cross": wrapped["cross"], "cui": wrapped["cui"], "cti": wrapped["cti"], "head": wrapped["head"].module}
+        exchange = "torch DistributedDataParallel, one wrapper per module, default arguments (train.py:136-139); head via .module (train.py:251)"
+    elif distributed:
+        pkg.functional.enable_grad_allreduce()
+        exchange = "native flat-buffer all-reduce (functional.enable_grad_allreduce)"
+
     # ---------------- device-resident timing ----------------
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(W):
         step(resident)
     barrier()
     L.mmoe_gemm_timing(128 * args.steps)           # event pairs for the roofline pass are created up front
@@ -380,34 +536,9 @@ def main():
     gc.collect()
     gc.disable()          # a generation-2 collection inside a timed loop stalls the enqueueing thread for tens of ms
 
-    def timed_loop():
-        """K steps bracketed by barrier + synchronize; returns (total ms, sorted per-step ms, slowest index, host stats)."""
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-        for e in step_ev:
-            e.record()            # torch creates the CUDA event lazily at the first record: do that outside the timed loop
-        barrier()
-        ev0.record()
-        t_host = time.perf_counter()
-        step_ev[0].record()
-        host_t = [time.perf_counter()]
-        for i in range(args.steps):
-            if i >= 2 and not os.environ.get("BENCH_NO_THROTTLE"):
-                step_ev[i - 1].synchronize()   # stay at most two steps ahead of the device (bounded launch-queue depth)
-            step(resident)
-            step_ev[i + 1].record()
-            host_t.append(time.perf_counter())
-        host_ms = (time.perf_counter() - t_host) * 1e3 / args.steps      # time the host needs to ENQUEUE a step
-        ev1.record()
-        barrier()
-        per = [step_ev[i].elapsed_time(step_ev[i + 1]) for i in range(args.steps)]
-        slow = max(range(args.steps), key=lambda i: per[i])
-        per.sort()
-        return ev0.elapsed_time(ev1), per, slow, host_ms, max((host_t[i + 1] - host_t[i]) * 1e3 for i in range(args.steps))
-
     # pass 1 (the headline): no per-launch events
     L.mmoe_launch_count(1)
-    ms_total, per_step, slowest_step, host_ms_step, host_ms_max = timed_loop()
+    ms_total, per_step, slowest_step, host_ms_step, host_ms_max = timed_loop(args.steps)
     clocks = sampler.stop() if rank == 0 else None
     launches = int(L.mmoe_launch_count(1))
     # pass 2 (the roofline): the same K steps with a CUDA event pair around every GEMM launch.  Kept out of pass 1 because
@@ -415,15 +546,15 @@ def main():
     # ... and on one stream, so that no other kernel shares the SMs while a GEMM is being timed.
     use_side[0] = False
     L.mmoe_gemm_timing(1)
-    ms_total_ev, _, _, _, _ = timed_loop()
+    ms_total_ev, _, _, _, _ = timed_loop(args.steps)
     L.mmoe_gemm_timing(0)
     use_side[0] = side_stream is not None
+    n_rec = L.mmoe_gemm_timing_dump(None, 0)
+    rows = (C.c_double * (10 * max(n_rec, 1)))()
+    L.mmoe_gemm_timing_dump(rows, n_rec)
     g_ms, g_fl, g_n = C.c_double(), C.c_double(), C.c_int64()
     L.mmoe_gemm_timing_read(C.byref(g_ms), C.byref(g_fl), C.byref(g_n), 1)
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if distributed:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    ms_step = max_over_ranks(ms_total) / args.steps
     value = B * world / (ms_step * 1e-3)
 
     # ---------------- end-to-end timing: pinned host -> device every step, loss read back ----------------
@@ -480,17 +611,13 @@ def main():
     e2e_loop(5)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    t0 = time.perf_counter()
     ev0.record()
     last_loss = e2e_loop(args.steps)
     ev1.record()
     barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
     e_ms = max(ev0.elapsed_time(ev1), 0.0)
-    t = torch.tensor([e_ms], device=dev, dtype=torch.float64)
-    if distributed:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = B * world / (float(t.item()) / args.steps * 1e-3)
+    e2e_value = B * world / (max_over_ranks(e_ms) / args.steps * 1e-3)
+    gc.enable()
 
     if rank == 0:
         peaks = {}
@@ -498,41 +625,102 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS, measured)" if peaks else "fallback 1400 TFLOP/s sustained (B200_PROFILING.md)"
-        achieved = (g_fl.value / (g_ms.value * 1e-3)) / 1e12 if g_ms.value > 0 else 0.0
+        sustained = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        burst = float(peaks.get("bf16_tflops", 1590.0))
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        # the burst peak was measured at full clock, the sustained one power-capped at ~1.36 GHz: use the one whose clock
+        # regime matches what the sampler saw during the timed region
+        full_clock = bool(clocks and clocks.get("sm_mhz") and clocks["sm_mhz"] >= 0.97 * (clocks.get("sm_max_mhz") or 1e9)
+                          and "sw_power_cap" not in clocks.get("reasons", []))
+        peak_tf = burst if full_clock else sustained
+        src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+        peak_src = (f"{src} bf16_tflops (cuBLAS burst, measured at full clock) — the timed region ran at {clocks['sm_mhz']:.0f} MHz with no power cap"
+                    if full_clock else f"{src} bf16_tflops_sustained (cuBLAS, power-capped clock regime)")
+        # per-class breakdown of the event-timed GEMM launches
+        classes = {}
+        pair_ms = pair_fl = 0.0
+        for r in range(n_rec):
+            ms_, fl_, tc_, bn_, ctas_, npb_, M_, N_, K_, maj_ = (rows[10 * r + c] for c in range(10))
+            if not tc_:
+                continue
+            key = f"{int(M_)}x{int(N_)}x{int(K_)}|{'AB'[int(maj_) & 1]}{'AB'[(int(maj_) >> 1) & 1]}|g{int(npb_)}|bn{int(bn_)}c{int(ctas_)}"
+            c = classes.setdefault(key, [0, 0.0, 0.0])
+            c[0] += 1; c[1] += ms_; c[2] += fl_
+            if int(ctas_) == 2:
+                pair_ms += ms_; pair_fl += fl_
+        by_class = sorted(({"class": k, "launches_per_step": v[0] / args.steps, "us_per_launch": 1e3 * v[1] / v[0],
+                            "ms_per_step": v[1] / args.steps, "tflops": (v[2] / (v[1] * 1e-3) / 1e12) if v[1] > 0 else 0.0}
+                           for k, v in classes.items()), key=lambda d: -d["ms_per_step"])
+        all_tf = (g_fl.value / (g_ms.value * 1e-3)) / 1e12 if g_ms.value > 0 else 0.0
+        pair_tf = (pair_fl / (pair_ms * 1e-3)) / 1e12 if pair_ms > 0 else 0.0
+        traffic, traffic_note = None, "no ncu capture recorded for this build"
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
+            traffic, traffic_note = tj.get("traffic_bytes_per_launch"), tj.get("note")
+        except Exception:
+            pass
+        path_tf = FLOP_PER_SAMPLE * B * world / (ms_step * 1e-3) / 1e12 / world
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic", "config": workload_config(B, world),
+            "data": "synthetic", "config": workload_config(B, world) | {"gradient_exchange": exchange},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(host[0]), "d2h_bytes_per_step": 4,
-                    "note": "pinned host batch copied on a side stream (double buffered) every step; every step's loss copied to pinned host memory and read by the host one step later"},
+                    "note": "pinned host batch copied on a side stream (double buffered) every step — sentence vectors and ViT tokens shipped "
+                            "as bf16 and cast on the device, the rest fp32; every step's loss copied to pinned host memory and read by the "
+                            "host one step later"},
             "gpu_launches": launches,
             "host_enqueue_ms_per_step": host_ms_step,
             "ms_per_step_min_median_max": [per_step[0], per_step[len(per_step) // 2], per_step[-1]], "slowest_step": slowest_step,
             "host_ms_max_step": host_ms_max,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 grouped GEMM, all launches of the timed region)",
-                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                         "traffic": None,
-                         "traffic_note": "aggregate over 88 launches, so no single per-launch figure; ncu --set full of the FFN1 "
-                                         "768->3072 launch: 55 MB read + 147 MB written vs 255 MB algorithmic "
-                                         "(profiles/r01_gemm_final_ncu_full.md)",
-                         "peak_source": peak_src,
-                         "gemm_ms_per_step": g_ms.value / args.steps, "gemm_launches_per_step": g_n.value / args.steps,
+            "roofline": {"bound": "tensor",
+                         "kernel": "gemm_tc_kernel<256,*,2> — the CTA-pair (cta_group::2) tcgen05 GEMM, all of its launches in the timed region "
+                                   "(the dominant kernel: encoder-layer forward / dgrad / wgrad GEMMs)",
+                         "achieved": pair_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": pair_tf / peak_tf if peak_tf else None,
+                         "traffic": traffic, "traffic_note": traffic_note,
+                         "peak_source": peak_src, "frac_of_burst_peak": pair_tf / burst, "frac_of_sustained_peak": pair_tf / sustained,
+                         "pair_kernel_ms_per_step": pair_ms / args.steps,
+                         "all_gemm_launches": {"achieved": all_tf, "frac": all_tf / peak_tf, "ms_per_step": g_ms.value / args.steps,
+                                               "launches_per_step": g_n.value / args.steps},
+                         "by_class": by_class[:14],
                          "measured_over": "a second pass of the same K steps, single stream, with an event pair around every GEMM launch",
                          "ms_per_step_with_events": ms_total_ev / args.steps,
                          "gemm_share_of_step": (g_ms.value / ms_total_ev) if ms_total_ev else None,
-                         "path_tflops": FLOP_PER_SAMPLE * B / (ms_step * 1e-3) / 1e12,
-                         "path_frac_of_peak": FLOP_PER_SAMPLE * B / (ms_step * 1e-3) / 1e12 / peak_tf},
+                         "path_tflops": path_tf, "path_frac_of_peak": path_tf / peak_tf},
             "loss": last_loss,
         }
+        if native_result is not None:
+            line["native_exchange"] = native_result
+        if world == 1 and not args.no_extras:
+            # ---- the same step in eager PyTorch on this GPU (torch's own kernels), same weights ----
+            try:
+                from oracle import eager_ref as E
+                eager = {}
+                emods = E.make_v1_modules(dev, train=not args.eval_mode)
+                for k_, m_ in emods.items():                      # same weights as the native modules (identical state_dict keys)
+                    m_.load_state_dict({k: v for k, v in mods_d[k_].state_dict().items() if not k.startswith("backbone")}, strict=True)
+                for name, dt, reps in (("bf16_autocast", torch.bfloat16, 5), ("fp32", None, 2)):
+                    stp = eager_step_fn(emods, resident, dev, dt)
+                    ms_e = cuda_time(stp, 2, reps)
+                    eager[name] = {"ms_per_step": ms_e, "samples_per_s": B / ms_e * 1e3}
+                eager["speedup_bf16"] = eager["bf16_autocast"]["ms_per_step"] / ms_step
+                eager["what"] = ("the reference's module composition on stock torch.nn modules (oracle/eager_ref.py: nn.TransformerEncoderLayer, "
+                                 "nn.MultiheadAttention, nn.Linear, nn.LayerNorm called as the reference's forward bodies call them): "
+                                 "PyTorch-eager on this B200, train mode, same weights and batch, fwd+bwd")
+                line["eager_b200"] = eager
+                del emods, stp
+            except Exception as ex:  # noqa: BLE001
+                line["eager_b200"] = {"error": repr(ex)}
+            try:
+                line["extra"] = extra_measurements(dev, hbm, peak_tf)
+            except Exception as ex:  # noqa: BLE001
+                line["extra"] = {"error": repr(ex)}
         if not args.no_cpu_baseline and world == 1:
             try:
-                v, ms_cpu, cores = time_cpu_oracle(args.cpu_baseline_batch, 2, 1)
+                v, ms_cpu, cores, done_ = time_cpu_reference(args.cpu_baseline_batch, 2, 1, 60.0)
                 line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                        "sample": f"oracle/ port of the reference modules, fp32, {args.cpu_baseline_batch}-sample batch, "
-                                                  f"fwd+bwd, 2 timed steps ({ms_cpu:.0f} ms/step)"}
+                                        "sample": f"reference forward composition on stock torch.nn modules (oracle/eager_ref.py), fp32, train "
+                                                  f"mode, {args.cpu_baseline_batch}-sample batch, fwd+bwd, {done_} timed steps ({ms_cpu:.0f} ms/step)"}
             except Exception as ex:  # noqa: BLE001
                 line["cpu_baseline"] = {"error": repr(ex)}
         print(json.dumps(line), flush=True, file=_REAL_STDOUT or sys.stdout)

@@ -113,6 +113,10 @@ int mmoe_gemm_grouped(const mmoe_gemm_problem* problems /*host*/, int n_problems
  * enable > 1 also pre-creates event pairs for that many launches, so no event is created inside a timed region. */
 int mmoe_gemm_timing(int enable);
 int mmoe_gemm_timing_read(double* total_ms, double* total_flops, int64_t* launches, int tc_only);
+/* Per-launch records since the last _read, not cleared (call after a device synchronize and before _read): up to max_rows
+ * rows of 10 doubles {ms, 2*M*N*K summed over the launch, tensor-core launch?, tile width, CTAs per tile, problems in the
+ * launch, M, N, K of the first problem, its a_major | b_major << 1}.  Returns the number of records available. */
+int mmoe_gemm_timing_dump(double* rows, int max_rows);
 
 /* Launch trace of the tensor-core GEMM launches (tests: which kernel variant a shape resolved to).  enable != 0 clears the
  * record and starts recording, 0 stops.  _read copies up to max_entries records of 4 ints {tile width, CTAs per tile (2 =

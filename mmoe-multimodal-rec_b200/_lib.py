@@ -80,6 +80,7 @@ PROTOTYPES = {
     "mmoe_gemm_grouped": (C.c_int, [_P(GemmProblem), C.c_int, C.c_int, C.c_int, _vp]),
     "mmoe_gemm_timing": (C.c_int, [C.c_int]),
     "mmoe_gemm_timing_read": (C.c_int, [_P(C.c_double), _P(C.c_double), _P(_i64), C.c_int]),
+    "mmoe_gemm_timing_dump": (C.c_int, [_P(C.c_double), C.c_int]),
     "mmoe_set_sm_reserve": (C.c_int, [C.c_int]),
     "mmoe_launch_trace": (C.c_int, [C.c_int]),
     "mmoe_launch_trace_read": (C.c_int, [_P(_i32), C.c_int]),

@@ -996,6 +996,7 @@ static int fill_epi(EpiDev* d, const mmoe_gemm_problem& pr, int dtype) {
 }
 
 extern std::atomic<int> g_sm_reserve;
+static thread_local int t_last_bn, t_last_ctas;
 // launch trace (tests): which instantiation each tensor-core launch used
 struct TraceEntry { int bn, ctas, rich, tiles; };
 static std::mutex g_trace_mu;
@@ -1171,6 +1172,7 @@ static int launch_tc(const mmoe_gemm_problem* pr_in, int n, int dtype, cudaStrea
     kernels[bn == 64 ? 0 : (bn == 128 ? 1 : 2)][rich ? 1 : 0]<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(P);
   }
   MMOE_LAUNCH_OK("gemm_tc_kernel");
+  t_last_bn = bn; t_last_ctas = ctas;
   if (g_trace_on.load(std::memory_order_relaxed)) {
     std::lock_guard<std::mutex> lk(g_trace_mu);
     g_trace.push_back(TraceEntry{bn, ctas, rich ? 1 : 0, tiles});
@@ -1222,7 +1224,8 @@ static int launch_simt(const mmoe_gemm_problem* pr, int n, int dtype, cudaStream
 // live timing of the GEMM launches (bench.py's roofline): CUDA events recorded on the launching stream around
 // every grouped launch while enabled; read back after a synchronize.
 // ------------------------------------------------------------------------------------------
-struct TimedLaunch { cudaEvent_t a, b; double flops; int tc; };
+struct TimedLaunch { cudaEvent_t a, b; double flops; int tc; int bn, ctas, n_problems, M, N, K, a_major, b_major; };
+
 static std::mutex g_time_mu;
 static std::vector<TimedLaunch> g_timed;
 static std::vector<cudaEvent_t> g_event_pool;
@@ -1249,8 +1252,12 @@ int gemm_grouped(const mmoe_gemm_problem* problems, int n_problems, int dtype, i
     t.a = take_event(); t.b = take_event();
   }
   cudaEventRecord(t.a, stream);
+  t_last_bn = t_last_ctas = 0;
   const int rc = gemm_grouped_untimed(problems, n_problems, dtype, engine, stream);
   cudaEventRecord(t.b, stream);
+  // the first problem names the launch (the orchestrators put the dgrad / forward problem first)
+  t.bn = t_last_bn; t.ctas = t_last_ctas; t.n_problems = n_problems;
+  t.M = problems[0].M; t.N = problems[0].N; t.K = problems[0].K; t.a_major = problems[0].a_major; t.b_major = problems[0].b_major;
   std::lock_guard<std::mutex> lk(g_time_mu);
   g_timed.push_back(t);
   return rc;
@@ -1311,6 +1318,25 @@ extern "C" int mmoe_gemm_timing(int enable) {
   }
   mmoe::g_timing_on.store(enable ? 1 : 0);
   return 0;
+}
+// Per-launch records since the last read, without clearing them (call after a device synchronize, before _read): up to
+// max_rows rows of 10 doubles {ms, flops, tensor-core?, tile width, CTAs per tile, problems in the launch, M, N, K of the
+// first problem, its (a_major | b_major << 1)}.  Returns the number of records available.
+extern "C" int mmoe_gemm_timing_dump(double* rows, int max_rows) {
+  using namespace mmoe;
+  std::lock_guard<std::mutex> lk(g_time_mu);
+  int i = 0;
+  for (auto& t : g_timed) {
+    if (rows != nullptr && i < max_rows) {
+      float dt = 0.f;
+      cudaEventElapsedTime(&dt, t.a, t.b);
+      double* r = rows + 10 * (size_t)i;
+      r[0] = dt; r[1] = t.flops; r[2] = t.tc; r[3] = t.bn; r[4] = t.ctas; r[5] = t.n_problems; r[6] = t.M; r[7] = t.N; r[8] = t.K;
+      r[9] = t.a_major | (t.b_major << 1);
+    }
+    ++i;
+  }
+  return i;
 }
 // Sums over the launches recorded since the last read (call after a device synchronize); clears the record.
 extern "C" int mmoe_gemm_timing_read(double* total_ms, double* total_flops, int64_t* launches, int tc_only) {

@@ -223,7 +223,10 @@ def compare_with_oracle(case: C.Case, mode: str, module=None, stats: Optional[di
     """
     import mmoe_multimodal_rec_b200 as pkg
     Fn = pkg.functional
-    inject = mode != "fp32" and case.kind in ("cross", "cross_home", "fuse", "fuse_home")
+    # ReLU' is discontinuous at 0: with ~10^8 pre-activations per call (B >= 64) a handful lie within fp32 rounding of zero,
+    # and ONE flipped unit moves a row of d linear1.weight by ~1e-2 of the tensor's scale — so the activation pattern is
+    # injected in fp32 too once the batch is that large (and its disagreement with the fp64 pattern bounded separately)
+    inject = (mode != "fp32" or case.B >= 64) and case.kind in ("cross", "cross_home", "fuse", "fuse_home")
     if inject:
         Fn.DEBUG_SAVED = []
     drop = None

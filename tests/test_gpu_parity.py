@@ -61,7 +61,10 @@ def test_benchmark_sized_batches_match_oracle(case, mode):
     L.mmoe_launch_trace(0)
     _assert_ok(errs, PU.TOL[mode], f"{case.name} {mode}")
     if stats:
-        assert stats["flip_frac"] < 0.01 and stats["flip_max_rel_z"] < 0.05, stats
+        if mode == "fp32":     # fp32: the kernels' ReLU pattern may differ from the fp64 one only in entries that are ~0 in fp32
+            assert stats["flip_frac"] < 1e-5 and stats["flip_max_rel_z"] < 1e-5, stats
+        else:
+            assert stats["flip_frac"] < 0.01 and stats["flip_max_rel_z"] < 0.05, stats
     if mode != "fp32":
         assert n > 0           # the tensor-core engine ran
 
@@ -80,7 +83,8 @@ def test_cross_expert_at_the_benchmark_batch_uses_the_pair_kernel_and_matches():
     L.mmoe_launch_trace_read(buf, n)
     L.mmoe_launch_trace(0)
     pair = sum(1 for i in range(n) if buf[4 * i + 1] == 2)
-    assert pair >= 40, f"only {pair} of {n} GEMM launches used the CTA-pair kernel"
+    # 4 encoder layers x (4 forward + 4 backward) GEMM launches + the cross-attention projections (the [B, .] MLP stays small)
+    assert pair >= 32, f"only {pair} of {n} GEMM launches used the CTA-pair kernel"
     _assert_ok(errs, PU.TOL["bf16"], "cross_b512 bf16")
     assert stats["flip_frac"] < 0.01 and stats["flip_max_rel_z"] < 0.05, stats
 
