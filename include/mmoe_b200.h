@@ -270,6 +270,69 @@ size_t mmoe_img_proj_workspace_bytes(int32_t B, int32_t d, int32_t proj, int dty
 int mmoe_img_proj_fwd(const mmoe_call* c, int32_t d, int32_t proj, const float* img_vec, float* out);
 int mmoe_img_proj_bwd(const mmoe_call* c, int32_t d, int32_t proj, const float* dout, float* d_img_vec);
 
+/* ---- the callers and data formats either side of the path ------------------------------------------ */
+
+/* HomeExpertWrapper x n + torch.stack — train_HoME.py:100-116 (Dropout(SiLU(BatchNorm1d(x)))) and :350-356 (six wrappers
+ * and the stack feeding HOME_MMoE_Complete), in one launch.  x: host array of n device pointers to fp32 [B, d];
+ * params = {norm_0.weight, norm_0.bias, ..., norm_{n-1}.weight, norm_{n-1}.bias}; running_mean / running_var: host arrays of n
+ * device pointers to the BatchNorm buffers (fp32 [d]), UPDATED in training (momentum, unbiased variance) and used as the
+ * statistics in eval; out fp32 [B, n, d]; save_mean / save_rstd fp32 [n, d] for the backward.  Dropout site 0 over the
+ * stacked [B, n, d] index.  Backward: dout fp32 [B, n, d]; dx host array of n fp32 [B, d] buffers (NULL entries / NULL = skip);
+ * grads as params, accumulated. */
+int mmoe_bn_silu_stack_fwd(const mmoe_call* c, int32_t n, int32_t d, const float* const* x, float* out, float* save_mean,
+                           float* save_rstd, float* const* running_mean, float* const* running_var, float momentum, float eps);
+int mmoe_bn_silu_stack_bwd(const mmoe_call* c, int32_t n, int32_t d, const float* const* x, const float* dout,
+                           const float* save_mean, const float* save_rstd, float* const* running_mean,
+                           float* const* running_var, float* const* dx, float eps);
+
+/* Two-task nn.BCEWithLogitsLoss(pos_weight) with mean reduction — train.py:189-192, 253-254: value and gradient in one
+ * launch over the head's logits [2, B] (good, best).  loss: 1 float on the device, ACCUMULATED into (zero it first);
+ * dlogits fp32 [2, B] or NULL; gscale multiplies the gradient. */
+int mmoe_bce2_fwd_bwd(const float* logits, const float* y_good, const float* y_best, float pos_weight_good,
+                      float pos_weight_best, int32_t B, float* loss, float* dlogits, float gscale, void* stream);
+
+/* calculate_contrastive_loss — train_HoME.py:43-51 (InfoNCE with in-batch negatives, temperature 0.07) for up to 4
+ * (anchor, positive) pairs at once (train_HoME.py:362-364 uses three): F.normalize rows, similarity GEMMs on the GEMM engine,
+ * cross-entropy against the diagonal.  anchor / positive: host arrays of n_pairs device pointers to fp32 [B, d]
+ * (B % 8 == 0, d % 8 == 0); loss: n_pairs floats on the device, ACCUMULATED into.  Backward: dloss = host array of the
+ * n_pairs upstream scalars; d_anchor / d_positive: host arrays of fp32 [B, d] device buffers ACCUMULATED into (an input
+ * used by several pairs passes the same buffer), NULL entries are skipped. */
+size_t mmoe_info_nce_saved_bytes(int32_t n_pairs, int32_t B, int32_t d, int dtype);
+size_t mmoe_info_nce_workspace_bytes(int32_t n_pairs, int32_t B, int32_t d, int dtype);
+int mmoe_info_nce_fwd(const mmoe_call* c, int32_t n_pairs, int32_t d, const float* const* anchor, const float* const* positive,
+                      float temperature, float* loss);
+int mmoe_info_nce_bwd(const mmoe_call* c, int32_t n_pairs, int32_t d, const float* const* anchor, const float* const* positive,
+                      const float* dloss, float* const* d_anchor, float* const* d_positive);
+
+/* ROC-AUC of n scores on the device — what inference_and_auc.py:150-178 computes with sklearn.metrics.roc_auc_score after
+ * copying every batch to the host: sort + rank-sum with average ranks for ties.  scores, labels fp32 [n] (label > 0.5 =
+ * positive); out: 1 double on the device (NaN when a class is empty). */
+size_t mmoe_auc_workspace_bytes(int64_t n);
+int mmoe_auc(const float* scores, const float* labels, int64_t n, void* workspace, size_t workspace_bytes, double* out, void* stream);
+
+/* Patch projection — the Conv2d(3,768,16,stride 16) of HF ViTPatchEmbeddings reached by ItemImageExpert's backbone call
+ * (model.py:373-376) as a GEMM over patch-major rows [B*196, C*16*16], the on-disk layout of newpatch.py:102-104 /
+ * data4model.py:254-258 (patch.bin).  _u8_to_operand: raw patch bytes -> T rows holding the byte values 0..255 (exact in 16
+ * bits; the caller folds /255, mean and std of model.py:172-174 into weight and bias).  _patchify: normalised float images
+ * [B,C,H,W] -> the same row layout.  _project: out[rows,N] = operand[rows,K] weight[N,K]^T + bias on the GEMM engine. */
+int mmoe_patch_u8_to_operand(const uint8_t* patches, void* out, int64_t rows, int32_t k, int dtype, void* stream);
+int mmoe_patchify(const float* images, void* out, int32_t B, int32_t C, int32_t H, int32_t W, int32_t p, int dtype, void* stream);
+int mmoe_patch_project(const void* operand, const void* weight, const float* bias, void* out, int out_dtype, int64_t rows,
+                       int32_t N, int32_t K, int dtype, void* stream);
+
+/* TextExpert.forward after the encoder — model.py:286-338 (gather the <SENT> hidden states, bucket per sample, pad to S
+ * slots, data-derived padding mask, masked mean, LayerNorm, dropout); HoME variant model_HoME.py:328-369 (params = NULL: no
+ * final LayerNorm / dropout).  h: encoder hidden states as rows of d values (fp32 or T); src int32 [B, S]: row of h feeding
+ * slot (b, s), -1 = empty slot (built on the host from chunk2sample / sent_pos); params = {norm.weight, norm.bias} or NULL.
+ * Dropout sites: 0 sentence rows [B,S,d], 1 doc vectors [B,d].  Outputs: sent fp32 [B,S,d], mask uint8 [B,S] (1 = padding),
+ * doc fp32 [B,d]; saved for backward: pre_doc fp32 [B,d], stats fp32 [B*(S+1), 2].  Backward: dh fp32 [rows of h, d]
+ * ACCUMULATED into (zero first); grads = {d norm.weight, d norm.bias} or NULL. */
+int mmoe_sent_gather_fwd(const mmoe_call* c, int32_t S, int32_t d, const void* h, int h_dtype, const int32_t* src,
+                         float* sent, uint8_t* mask, float* doc, float* pre_doc, float* stats);
+int mmoe_sent_gather_bwd(const mmoe_call* c, int32_t S, int32_t d, const void* h, int h_dtype, const int32_t* src,
+                         const uint8_t* mask, const float* pre_doc, const float* stats, const float* d_sent,
+                         const float* d_doc, float* dh);
+
 #ifdef __cplusplus
 }
 #endif

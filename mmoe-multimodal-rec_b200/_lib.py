@@ -118,6 +118,20 @@ PROTOTYPES = {
     "mmoe_img_proj_workspace_bytes": (_sz, [_i32, _i32, _i32, C.c_int]),
     "mmoe_img_proj_fwd": (C.c_int, [_P(Call), _i32, _i32, _vp, _vp]),
     "mmoe_img_proj_bwd": (C.c_int, [_P(Call), _i32, _i32, _vp, _vp]),
+    "mmoe_bn_silu_stack_fwd": (C.c_int, [_P(Call), _i32, _i32, _P(_vp), _vp, _vp, _vp, _P(_vp), _P(_vp), _f, _f]),
+    "mmoe_bn_silu_stack_bwd": (C.c_int, [_P(Call), _i32, _i32, _P(_vp), _vp, _vp, _vp, _P(_vp), _P(_vp), _P(_vp), _f]),
+    "mmoe_bce2_fwd_bwd": (C.c_int, [_vp, _vp, _vp, _f, _f, _i32, _vp, _vp, _f, _vp]),
+    "mmoe_info_nce_saved_bytes": (_sz, [_i32, _i32, _i32, C.c_int]),
+    "mmoe_info_nce_workspace_bytes": (_sz, [_i32, _i32, _i32, C.c_int]),
+    "mmoe_info_nce_fwd": (C.c_int, [_P(Call), _i32, _i32, _P(_vp), _P(_vp), _f, _vp]),
+    "mmoe_info_nce_bwd": (C.c_int, [_P(Call), _i32, _i32, _P(_vp), _P(_vp), _P(_f), _P(_vp), _P(_vp)]),
+    "mmoe_auc_workspace_bytes": (_sz, [_i64]),
+    "mmoe_auc": (C.c_int, [_vp, _vp, _i64, _vp, _sz, _vp, _vp]),
+    "mmoe_patch_u8_to_operand": (C.c_int, [_vp, _vp, _i64, _i32, C.c_int, _vp]),
+    "mmoe_patchify": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, C.c_int, _vp]),
+    "mmoe_patch_project": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _i64, _i32, _i32, C.c_int, _vp]),
+    "mmoe_sent_gather_fwd": (C.c_int, [_P(Call), _i32, _i32, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mmoe_sent_gather_bwd": (C.c_int, [_P(Call), _i32, _i32, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libmmoe_b200.so")
-SOURCES = ["gemm.cu", "kernels.cu", "attention.cu", "attention_tc.cu", "cross.cu", "fuse.cu", "head.cu", "home.cu", "img.cu"]
+SOURCES = ["gemm.cu", "kernels.cu", "attention.cu", "attention_tc.cu", "cross.cu", "fuse.cu", "head.cu", "home.cu", "img.cu", "wrap.cu", "tail.cu", "ingest.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math" if os.environ.get("MMOE_FAST_MATH") else "-DMMOE_EXACT_MATH"]

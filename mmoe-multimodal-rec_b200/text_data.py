@@ -171,24 +171,22 @@ class TextExpert(nn.Module):
         else:
             with torch.no_grad():
                 h = self.encoder(**kwargs).last_hidden_state
-        # hidden states at the <SENT> markers; padded slots (-1) are zero rows
-        pos = torch.tensor(sent_pos, device=device)
-        n_chunks, per_chunk = pos.shape
+        if h.is_cuda:
+            # one native launch: gather the <SENT> rows, bucket, pad, mask, mean, LayerNorm, dropout (csrc/ingest.cu)
+            from .ingest import sentence_gather
+            return sentence_gather(h, chunk2sample, sent_pos, max_sent_count, self.norm if self.final_norm else None,
+                                   float(self.dropout.p), self.training)
+        return self._gather_torch(h, chunk2sample, sent_pos, max_sent_count)
+
+    def _gather_torch(self, h, chunk2sample, sent_pos, max_sent_count: int):
+        """The same step with torch ops, for an encoder that lives on the CPU (the text experts are reference torch modules and
+        not part of the native path; on CUDA the native kernel above always runs)."""
+        from .ingest import build_slot_table
+        device = h.device
         D = h.size(-1)
-        rows = torch.arange(n_chunks, device=device).unsqueeze(1).expand(n_chunks, per_chunk)
-        vecs = h[rows, pos.clamp(min=0, max=h.size(1) - 1)].masked_fill(pos.unsqueeze(-1) < 0, 0.0)
-        # chunk i of a sample occupies sentence slots [rank_i*per_chunk, (rank_i+1)*per_chunk), cut at max_sent_count
-        owner = torch.tensor(chunk2sample, device=device, dtype=torch.long)
-        B = int(owner.max().item()) + 1
-        rank = torch.zeros(n_chunks, dtype=torch.long, device=device)
-        seen = {}
-        for i, s in enumerate(chunk2sample):
-            rank[i] = seen.get(s, 0)
-            seen[s] = seen.get(s, 0) + 1
-        slot = rank.unsqueeze(1) * per_chunk + torch.arange(per_chunk, device=device).unsqueeze(0)
-        ok = slot < max_sent_count
-        padded = torch.zeros(B, max_sent_count, D, device=device, dtype=vecs.dtype)
-        padded = padded.index_put((owner.unsqueeze(1).expand_as(slot)[ok], slot[ok]), vecs[ok])
+        src = build_slot_table(chunk2sample, sent_pos, h.size(1), max_sent_count).to(device).long()
+        rows = torch.cat([h.reshape(-1, D), torch.zeros(1, D, device=device, dtype=h.dtype)], 0)
+        padded = rows[torch.where(src >= 0, src, torch.full_like(src, rows.size(0) - 1))]
         sent_mask = padded.abs().sum(-1) == 0
         lens = (~sent_mask).sum(dim=1, keepdim=True)
         doc = padded.sum(dim=1) / lens.clamp(min=1)

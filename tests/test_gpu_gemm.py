@@ -117,9 +117,9 @@ def test_forward_linear_at_benchmark_shapes(name, M, dt):
         stored = out != 0
         assert bool((got | ~stored).all())                       # every stored non-zero has its bit
         # the bit is taken from the fp32 value before the 16-bit rounding: it may also be set where a tiny positive value
-        # underflowed to 0 in fp16 (ReLU' is 1 there, as in the reference); nowhere else
+        # (within the fp32 accumulation noise of zero) underflowed to 0 in fp16 — ReLU' is 1 there, as in the reference
         extra = got & ~stored
-        assert int(extra.sum()) <= 64 and (not bool(extra.any()) or float(ref[extra].abs().max()) < 2.0 ** -23)
+        assert int(extra.sum()) <= 64 and (not bool(extra.any()) or float(ref[extra].abs().max()) < 4e-6 * float(ref.abs().max()))
 
 
 def _trace(lib):
