@@ -108,6 +108,23 @@ def install_native_patch_embeddings(vit: nn.Module) -> nn.Module:
     return vit
 
 
+def vit_tokens_from_patch_bytes(vit: nn.Module, patch_bytes: torch.Tensor) -> torch.Tensor:
+    """last_hidden_state [B, 1 + patches, hidden] of an HF ``ViTModel`` fed with raw patch bytes (uint8 [B, patches, C*p*p], the
+    patch.bin layout): native patch projection with the normalisation folded into the weights, then the model's own
+    cls token / position embeddings / encoder / final LayerNorm.  (HF's ``ViTModel.forward`` insists on [B,C,H,W] pixel
+    values, so the byte path enters one level below it.)"""
+    emb = vit.embeddings
+    if not isinstance(emb.patch_embeddings, NativePatchEmbeddings):
+        install_native_patch_embeddings(vit)
+    x = emb.patch_embeddings(patch_bytes)
+    cls = emb.cls_token.expand(x.shape[0], -1, -1).to(x.dtype)
+    x = torch.cat((cls, x), dim=1) + emb.position_embeddings
+    x = emb.dropout(x)
+    out = vit.encoder(x)
+    h = out.last_hidden_state if hasattr(out, "last_hidden_state") else out[0]
+    return vit.layernorm(h)
+
+
 def decode_patch_bytes(patch_bytes: torch.Tensor) -> torch.Tensor:
     """Device-side form of decode_sample's image branch (model.py:160-178) for the v1 scripts' [B,3,224,224] contract:
     uint8 [B,196,768] patch bytes -> normalised float image [B,3,224,224].  Only needed by callers that want the float

@@ -217,11 +217,18 @@ class ItemImageExpert(nn.Module):
         self.dropout = nn.Dropout(dropout_p)
         self.norm = nn.LayerNorm(base_model.config.hidden_size)
 
+    def _tokens(self, images):
+        if images.dtype == torch.uint8:
+            # raw patch bytes [B, 196, 768] as stored on disk (newpatch.py:102-104): no un-patchify / normalise round trip
+            from .ingest import vit_tokens_from_patch_bytes
+            return vit_tokens_from_patch_bytes(self.backbone, images)
+        return self.backbone(pixel_values=images).last_hidden_state
+
     def forward(self, images: torch.Tensor, trainable: bool = False):
         if trainable:
-            tokens = self.backbone(pixel_values=images).last_hidden_state
+            tokens = self._tokens(images)
         else:
             with torch.no_grad():
-                tokens = self.backbone(pixel_values=images).last_hidden_state
+                tokens = self._tokens(images)
         return Fn.ImgPoolFn.apply(self.pool_type == "cls", self.training, float(self.dropout.p), tokens,
                                   self.norm.weight, self.norm.bias)

@@ -13,6 +13,7 @@ none of which the hot-path classes use; empty stand-ins are pre-seeded in
 """
 from __future__ import annotations
 
+import importlib.machinery
 import importlib.util
 import os
 import sys
@@ -32,6 +33,7 @@ def _stub(name: str, **attrs):
         return importlib.import_module(name)
     except Exception:
         m = types.ModuleType(name)
+        m.__spec__ = importlib.machinery.ModuleSpec(name, None)     # importlib.util.find_spec() on a stub must not raise
         m.__dict__.update(attrs)
         sys.modules[name] = m
         return m
@@ -49,18 +51,45 @@ def _install_stubs():
     _stub("matplotlib.pyplot")
 
 
+_STUB_NAMES = ("webdataset", "peft", "nltk", "nltk.tokenize", "matplotlib", "matplotlib.pyplot")
+
+
 def load_reference(which: str = "model"):
-    """Return the reference module object (``model`` or ``model_HoME``) under a
-    private name so it never shadows the drop-in ``model.py`` at the repo root."""
+    """Return the reference module object (``model``, ``model_HoME``, or a script such as ``train_HoME``) under a private
+    name so it never shadows the drop-in ``model.py`` at the repo root.  The stand-ins for the missing third-party modules
+    are visible in ``sys.modules`` only while the file is being imported (the reference module keeps its own references)."""
     if not reference_available():
         raise FileNotFoundError(f"reference not mounted at {REFERENCE_DIR}")
     alias = f"_reference_{which}"
     if alias in sys.modules:
         return sys.modules[alias]
-    _install_stubs()
-    path = os.path.join(REFERENCE_DIR, which + ".py")
-    spec = importlib.util.spec_from_file_location(alias, path)
-    mod = importlib.util.module_from_spec(spec)
-    sys.modules[alias] = mod
-    spec.loader.exec_module(mod)
-    return mod
+    before = {n: sys.modules.get(n) for n in _STUB_NAMES + ("model", "model_HoME")}
+    try:
+        try:
+            # transformers resolves these lazily and probes for `peft` while doing so: let it, before the stub exists
+            from transformers import AutoModel, AutoTokenizer, ViTConfig, ViTModel, get_linear_schedule_with_warmup  # noqa: F401
+        except Exception:
+            pass
+        _install_stubs()
+        if which in ("train_HoME", "infer_auc_HoME"):            # scripts do `from model_HoME import ...`
+            sys.modules["model_HoME"] = load_reference("model_HoME")
+            _install_stubs()
+        if which in ("train", "inference_and_auc"):
+            sys.modules["model"] = load_reference("model")
+            _install_stubs()
+        mp = sys.modules["matplotlib"]
+        if not hasattr(mp, "use"):
+            mp.use = lambda *a, **k: None
+        path = os.path.join(REFERENCE_DIR, which + ("" if which == "infer_auc_HoME" else ".py"))
+        loader = importlib.machinery.SourceFileLoader(alias, path)
+        spec = importlib.util.spec_from_loader(alias, loader)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[alias] = mod
+        spec.loader.exec_module(mod)
+        return mod
+    finally:
+        for n, m in before.items():
+            if m is None:
+                sys.modules.pop(n, None)
+            else:
+                sys.modules[n] = m
