@@ -107,7 +107,8 @@ static NceLayout nce_layout(char* saved, char* work, int n, int B, int d, size_t
 // key = order-preserving map of the float score to uint32, word = key << 1 | label  (so equal scores sort negatives first;
 // tie groups are recovered from the key alone)
 __device__ __forceinline__ uint32_t float_key(float f) {
-  const uint32_t u = __float_as_uint(f);
+  uint32_t u = __float_as_uint(f);
+  if ((u << 1) == 0u) u = 0u;                     // -0.0 and +0.0 are one value (a tie), not neighbours
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 __global__ void auc_pack_kernel(const float* __restrict__ score, const float* __restrict__ label, uint64_t* __restrict__ w, int n, int n_pad) {
