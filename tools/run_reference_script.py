@@ -158,6 +158,15 @@ class FakeLora(torch.nn.Module):
 
 
 def install_environment():
+    # transformers resolves its classes lazily and probes sys.modules while doing so: import what is needed BEFORE any stand-in
+    # module exists
+    import transformers
+    from transformers import AutoModel, AutoTokenizer, BertConfig, BertModel, ViTConfig, ViTModel, get_linear_schedule_with_warmup  # noqa: F401
+    AutoTokenizer.from_pretrained = staticmethod(lambda name, **k: FakeTokenizer())
+    AutoModel.from_pretrained = staticmethod(lambda name, **k: BertModel(BertConfig(
+        vocab_size=30522, hidden_size=768, num_hidden_layers=1, num_attention_heads=12, intermediate_size=512)))
+    ViTModel.from_pretrained = classmethod(lambda cls, name, **k: ViTModel(ViTConfig(num_hidden_layers=2)))
+
     class _Plt(types.ModuleType):
         def __getattr__(self, k):
             return lambda *a, **kw: None
@@ -171,12 +180,6 @@ def install_environment():
         plt.__spec__ = importlib.machinery.ModuleSpec("matplotlib.pyplot", None)
         sys.modules["matplotlib.pyplot"] = plt
         _module("matplotlib", use=lambda *a, **k: None, pyplot=plt)
-    import transformers
-    from transformers import AutoModel, AutoTokenizer, BertConfig, BertModel, ViTConfig, ViTModel, get_linear_schedule_with_warmup  # noqa: F401
-    AutoTokenizer.from_pretrained = staticmethod(lambda name, **k: FakeTokenizer())
-    AutoModel.from_pretrained = staticmethod(lambda name, **k: BertModel(BertConfig(
-        vocab_size=30522, hidden_size=768, num_hidden_layers=1, num_attention_heads=12, intermediate_size=512)))
-    ViTModel.from_pretrained = classmethod(lambda cls, name, **k: ViTModel(ViTConfig(num_hidden_layers=2)))
     os.environ.setdefault("RANK", "0"); os.environ.setdefault("WORLD_SIZE", "1"); os.environ.setdefault("LOCAL_RANK", "0")
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29577")
     return transformers
