@@ -230,6 +230,7 @@ struct CrossScratch {
   EncScratch enc;
   float *dU, *dI, *dpooled, *dnormed; void *dC, *dctx, *dq, *dkv, *g, *dz;
   void *hand_u, *hand_i;       // EncHandoff buffers of the user / item stack (separate: the two stacks' stage calls may interleave)
+  void *dUq, *dIt;             // 16-bit dgrads of the cross-attention projections: dq Wq (added to dU) and dkv Wkv (= dI)
 };
 static CrossScratch cross_scratch_layout(Arena& A, const mmoe_cross_cfg& cfg, int B, int dtype) {
   CrossScratch t{};
@@ -240,6 +241,7 @@ static CrossScratch cross_scratch_layout(Arena& A, const mmoe_cross_cfg& cfg, in
   t.dC = A.take(M * d * es); t.dctx = A.take(M * d * es); t.dq = A.take(M * d * es); t.dkv = A.take(M * 2 * d * es);
   t.g = A.take((size_t)B * d * es); t.dz = A.take((size_t)B * ff * es);
   t.hand_u = A.take(M * d * es); t.hand_i = A.take(M * d * es);
+  t.dUq = A.take(M * d * es); t.dIt = A.take(M * d * es);
   return t;
 }
 
@@ -470,9 +472,11 @@ extern "C" int mmoe_cross_bwd_stage(const mmoe_call* c, const mmoe_cross_cfg* cf
     MMOE_TRY(attention_bwd(a, st));
   }
   {
+    // 16-bit outputs through the TMA-store epilogue (the fp32 read-modify-write epilogue made this launch epilogue-bound:
+    // 402 us for 232 GFLOP); the encoder stacks take them as an extra summand of their output gradient
     mmoe_epilogue eu = epi_none(), ei = epi_none();
-    eu.out = t.dU; eu.out_dtype = MMOE_F32; eu.ldo = d; eu.residual = t.dU; eu.ld_res = d;   // dU += dq Wq
-    ei.out = t.dI; ei.out_dtype = MMOE_F32; ei.ldo = d;                                       // dI  = dkv Wkv
+    eu.out = t.dUq; eu.out_dtype = dtype; eu.ldo = d;       // dq Wq   (dU = pooling gradient + this)
+    ei.out = t.dIt; ei.out_dtype = dtype; ei.ldo = d;       // dkv Wkv (= dI)
     mmoe_gemm_problem p[4] = {
         linear_dgrad(t.dq, d, w_in, M, d, d, eu),
         linear_dgrad(t.dkv, 2 * d, w_in + (size_t)d * d * es, M, 2 * d, d, ei),
@@ -490,16 +494,18 @@ extern "C" int mmoe_cross_bwd_stage(const mmoe_call* c, const mmoe_cross_cfg* cf
     ec.mask = item_mask; ec.site0 = 16 * l + 8;
     const float* x_in = l == 0 ? item : s.item[l].x_sum;
     EncHandoff below{t.hand_i, l > 0 ? enc_g(G + ix.item0 + 12 * (l - 1)).b2 : nullptr, (uint32_t)(16 * (l - 1) + 8)};
-    MMOE_TRY(enc_bwd(ec, enc_w(P + ix.item0 + 12 * l), enc_g(G + ix.item0 + 12 * l), x_in, s.item[l], t.enc, t.dI,
-                     l == 0 ? d_item : t.dI, l < cfg->n_layer - 1 ? t.hand_i : nullptr, l > 0 ? &below : nullptr));
+    const bool top = l == cfg->n_layer - 1;     // the top layer's output gradient is the 16-bit dkv Wkv alone
+    MMOE_TRY(enc_bwd(ec, enc_w(P + ix.item0 + 12 * l), enc_g(G + ix.item0 + 12 * l), x_in, s.item[l], t.enc, top ? nullptr : t.dI,
+                     l == 0 ? d_item : t.dI, top ? nullptr : t.hand_i, l > 0 ? &below : nullptr, top ? t.dIt : nullptr));
   }
   for (int l = cfg->n_layer - 1; l >= 0; --l) {
     if (!(stage == -1 || stage == 100 + l)) continue;
     ec.mask = user_mask; ec.site0 = 16 * l;
     const float* x_in = l == 0 ? user : s.user[l].x_sum;
     EncHandoff below{t.hand_u, l > 0 ? enc_g(G + ix.user0 + 12 * (l - 1)).b2 : nullptr, (uint32_t)(16 * (l - 1))};
+    const bool top = l == cfg->n_layer - 1;     // top layer: pooling gradient (fp32) + 16-bit dq Wq
     MMOE_TRY(enc_bwd(ec, enc_w(P + ix.user0 + 12 * l), enc_g(G + ix.user0 + 12 * l), x_in, s.user[l], t.enc, t.dU,
-                     l == 0 ? d_user : t.dU, l < cfg->n_layer - 1 ? t.hand_u : nullptr, l > 0 ? &below : nullptr));
+                     l == 0 ? d_user : t.dU, top ? nullptr : t.hand_u, l > 0 ? &below : nullptr, top ? t.dUq : nullptr));
   }
   return 0;
 }

@@ -179,11 +179,13 @@ struct EncHandoff {
   uint32_t site0;       // dropout site base of the layer below
 };
 
-// dy: gradient w.r.t. the layer output (fp32 [M,d]); dx: gradient w.r.t. the layer input (fp32, may alias dy).
-// dy16: if non-null, the layer above already produced cast_drop(dy) and d b2 (EncHandoff).  below: if non-null, do the same
-// for the layer below.
+// dy (+ dy_t): gradient w.r.t. the layer output — fp32 [M,d] and/or a 16-bit [M,d] summand (a dgrad GEMM's output taken
+// straight from its fast 16-bit epilogue instead of an fp32 read-modify-write); dx: gradient w.r.t. the layer input (fp32,
+// may alias dy).  dy16: if non-null, the layer above already produced cast_drop(dy) and d b2 (EncHandoff).  below: if
+// non-null, do the same for the layer below.
 inline int enc_bwd(const EncCtx& c, const EncW& w, const EncG& g, const float* x_in, const EncSaved& s, const EncScratch& t,
-                   const float* dy, float* dx, const void* dy16 = nullptr, const EncHandoff* below = nullptr) {
+                   const float* dy, float* dx, const void* dy16 = nullptr, const EncHandoff* below = nullptr,
+                   const void* dy_t = nullptr) {
   const int d = c.d, ff = c.ff; const int M = (int)c.M;
   const size_t es = dtype_size(c.dtype);
   uint32_t k0, k1;
@@ -191,7 +193,7 @@ inline int enc_bwd(const EncCtx& c, const EncW& w, const EncG& g, const float* x
   const void* g2 = dy16;
   if (g2 == nullptr) {
     site_keys(c.seed, c.site0 + 3, &k0, &k1);
-    MMOE_TRY(cast_drop_colsum(dy, t.g, g.b2, M, d, c.drop_p, k0, k1, c.dtype, c.stream));
+    MMOE_TRY(cast_drop_colsum(dy, t.g, g.b2, M, d, c.drop_p, k0, k1, c.dtype, c.stream, dy_t));
     g2 = t.g;
   }
   const bool bits = gemm_bitmask_supported(c.dtype, M, ff);
@@ -217,7 +219,7 @@ inline int enc_bwd(const EncCtx& c, const EncW& w, const EncG& g, const float* x
   {
     LnBwdArgs a{};
     a.dy = t.dxn; a.dy_dtype = c.dtype; a.x = s.x1; a.x_dtype = MMOE_F32; a.stats = s.st2; a.gamma = w.ln2_w;
-    a.dres = dy; a.dx = t.dx1; a.dgamma = g.ln2_w; a.dbeta = g.ln2_b; a.g_out = t.g; a.g_colsum = g.b_out;
+    a.dres = dy; a.dres_t = dy_t; a.dx = t.dx1; a.dgamma = g.ln2_w; a.dbeta = g.ln2_b; a.g_out = t.g; a.g_colsum = g.b_out;
     site_keys(c.seed, c.site0 + 1, &k0, &k1);
     a.drop_p = c.drop_p; a.k0 = k0; a.k1 = k1; a.rows = M; a.d = d; a.dtype = c.dtype;
     MMOE_TRY(layernorm_bwd(a, c.stream));

@@ -86,14 +86,15 @@ int cast_f32(const float* x, void* y, int64_t n, int dtype, cudaStream_t s) {
 // ---------------------------------------------------------------- cast + dropout + column sums
 // block = 256 threads, owns a panel of `rpb` rows x 1024 columns (blockIdx.y); thread t owns 4 adjacent columns
 template <typename T>
-__global__ void cast_drop_colsum_kernel(const float* __restrict__ x, T* __restrict__ g, float* __restrict__ colsum,
+__global__ void cast_drop_colsum_kernel(const float* __restrict__ x, const T* __restrict__ x_t, T* __restrict__ g, float* __restrict__ colsum,
                                         int64_t rows, int cols, uint32_t thresh, float scale, uint32_t k0, uint32_t k1, int rpb) {
   const int64_t r0 = (int64_t)blockIdx.x * rpb;
   const int64_t r1 = min(rows, r0 + rpb);
   for (int c = blockIdx.y * 1024 + threadIdx.x * 4; c < min(cols, (int)(blockIdx.y + 1) * 1024); c += 1024) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int64_t r = r0; r < r1; ++r) {
-      float4 v = load4<float>(x + r * cols + c);
+      float4 v = x != nullptr ? load4<float>(x + r * cols + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (x_t != nullptr) { const float4 e = load4<T>(x_t + r * cols + c); v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w; }
       if (thresh != 0) {
         const uint64_t idx = (uint64_t)r * cols + c;
         v.x = drop_keep(k0, k1, idx + 0, thresh) ? v.x * scale : 0.f;
@@ -127,16 +128,17 @@ static int panel_rows(int64_t rows, int cols) {
 }
 
 int cast_drop_colsum(const float* x, void* g, float* colsum, int64_t rows, int cols, float drop_p, uint32_t k0, uint32_t k1,
-                     int dtype, cudaStream_t s) {
+                     int dtype, cudaStream_t s, const void* x_t) {
   if (rows == 0) return 0;
   MMOE_CHECK(cols % 4 == 0, "cast_drop_colsum: cols must be a multiple of 4");
+  MMOE_CHECK(x != nullptr || x_t != nullptr, "cast_drop_colsum: no input");
   const uint32_t thresh = drop_p > 0.f ? drop_threshold(drop_p) : 0u;
   const float scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const int rpb = panel_rows(rows, cols);
   const dim3 grid((unsigned)((rows + rpb - 1) / rpb), (unsigned)((cols + 1023) / 1024));
-  if (dtype == MMOE_BF16) cast_drop_colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(x, (__nv_bfloat16*)g, colsum, rows, cols, thresh, scale, k0, k1, rpb);
-  else if (dtype == MMOE_F16) cast_drop_colsum_kernel<__half><<<grid, 256, 0, s>>>(x, (__half*)g, colsum, rows, cols, thresh, scale, k0, k1, rpb);
-  else cast_drop_colsum_kernel<float><<<grid, 256, 0, s>>>(x, (float*)g, colsum, rows, cols, thresh, scale, k0, k1, rpb);
+  if (dtype == MMOE_BF16) cast_drop_colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(x, (const __nv_bfloat16*)x_t, (__nv_bfloat16*)g, colsum, rows, cols, thresh, scale, k0, k1, rpb);
+  else if (dtype == MMOE_F16) cast_drop_colsum_kernel<__half><<<grid, 256, 0, s>>>(x, (const __half*)x_t, (__half*)g, colsum, rows, cols, thresh, scale, k0, k1, rpb);
+  else cast_drop_colsum_kernel<float><<<grid, 256, 0, s>>>(x, (const float*)x_t, (float*)g, colsum, rows, cols, thresh, scale, k0, k1, rpb);
   MMOE_LAUNCH_OK("cast_drop_colsum_kernel");
   return 0;
 }
@@ -321,7 +323,7 @@ int relu_mask_colsum(void* g, const void* h, float* colsum, int64_t rows, int co
 
 // ---------------------------------------------------------------- LayerNorm backward
 struct LnBwdDev {
-  const void* dy; const void* x; const float* stats; const float* gamma; const float* dres;
+  const void* dy; const void* x; const float* stats; const float* gamma; const float* dres; const void* dres_t;
   float* dx; float* dgamma; float* dbeta; void* g_out; float* g_colsum;
   uint32_t thresh, k0, k1; float scale;
   int64_t rows; int d;
@@ -360,6 +362,10 @@ __global__ void __launch_bounds__(128, 3) ln_bwd_kernel(const LnBwdDev a) {
         xh[i] = load4<XT>(x + row * d + c);
         dg[i] = load4<DT_>(dy + row * d + c);
         if (a.dres != nullptr) rs[i] = load4<float>(a.dres + row * d + c);
+        if (a.dres_t != nullptr) {
+          const float4 e = load4<T>(reinterpret_cast<const T*>(a.dres_t) + row * d + c);
+          rs[i].x += e.x; rs[i].y += e.y; rs[i].z += e.z; rs[i].w += e.w;
+        }
       }
     }
     const float mean = a.stats[row * 2], rstd = a.stats[row * 2 + 1];
@@ -451,7 +457,7 @@ int layernorm_bwd(const LnBwdArgs& a, cudaStream_t s) {
   MMOE_CHECK(a.d % 4 == 0 && a.d <= LN_NV * 128, "layernorm_bwd: d must be a multiple of 4 and <= %d", LN_NV * 128);
   MMOE_CHECK((a.dgamma == nullptr) == (a.dbeta == nullptr), "layernorm_bwd: dgamma and dbeta go together");
   LnBwdDev dev;
-  dev.dy = a.dy; dev.x = a.x; dev.stats = a.stats; dev.gamma = a.gamma; dev.dres = a.dres;
+  dev.dy = a.dy; dev.x = a.x; dev.stats = a.stats; dev.gamma = a.gamma; dev.dres = a.dres; dev.dres_t = a.dres_t;
   dev.dx = a.dx; dev.dgamma = a.dgamma; dev.dbeta = a.dbeta; dev.g_out = a.g_out; dev.g_colsum = a.g_colsum;
   dev.thresh = a.drop_p > 0.f ? drop_threshold(a.drop_p) : 0u;
   dev.scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;

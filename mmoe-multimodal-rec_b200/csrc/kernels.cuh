@@ -7,9 +7,10 @@ namespace mmoe {
 // y = T(x), n elements
 int cast_f32(const float* x, void* y, int64_t n, int dtype, cudaStream_t s);
 
-// g[r,c] = T(dropmask(x[r,c]));  colsum[c] += sum_r g  (either output optional)
+// g[r,c] = T(dropmask(x[r,c] + x_t[r,c]));  colsum[c] += sum_r g  (either output optional; x fp32 and x_t (T) are both
+// optional summands, at least one must be given)
 int cast_drop_colsum(const float* x, void* g, float* colsum, int64_t rows, int cols, float drop_p, uint32_t k0,
-                     uint32_t k1, int dtype, cudaStream_t s);
+                     uint32_t k1, int dtype, cudaStream_t s, const void* x_t = nullptr);
 
 int dropout_mask(uint32_t k0, uint32_t k1, float p, int64_t n, uint8_t* out, cudaStream_t s);
 
@@ -33,6 +34,7 @@ struct LnBwdArgs {
   const void* x; int x_dtype;            // LN input
   const float* stats; const float* gamma;
   const float* dres;                     // optional
+  const void* dres_t;                    // optional second residual gradient, operand dtype T (added to dres)
   float* dx;                             // optional
   float* dgamma; float* dbeta;           // optional (both or none)
   void* g_out; float* g_colsum;          // optional

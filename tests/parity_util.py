@@ -226,7 +226,8 @@ def compare_with_oracle(case: C.Case, mode: str, module=None, stats: Optional[di
     # ReLU' is discontinuous at 0: with ~10^8 pre-activations per call (B >= 64) a handful lie within fp32 rounding of zero,
     # and ONE flipped unit moves a row of d linear1.weight by ~1e-2 of the tensor's scale — so the activation pattern is
     # injected in fp32 too once the batch is that large (and its disagreement with the fp64 pattern bounded separately)
-    inject = (mode != "fp32" or case.B >= 64) and case.kind in ("cross", "cross_home", "fuse", "fuse_home")
+    # (and, since the fp32 GEMMs run as six bf16 product terms with ~1e-6 relative noise, at any batch size)
+    inject = case.kind in ("cross", "cross_home", "fuse", "fuse_home")
     if inject:
         Fn.DEBUG_SAVED = []
     drop = None

@@ -20,7 +20,11 @@ def _assert_ok(errs, tol, what):
 
 @pytest.mark.parametrize("case", C.CASES, ids=IDS)
 def test_fp32_matches_oracle(case):
-    _assert_ok(PU.compare_with_oracle(case, "fp32"), PU.TOL["fp32"], f"{case.name} fp32")
+    stats = {}
+    _assert_ok(PU.compare_with_oracle(case, "fp32", stats=stats), PU.TOL["fp32"], f"{case.name} fp32")
+    if stats:
+        # ReLU pattern of the kernels vs the fp64 one: may differ only in entries that are zero to fp32 accuracy
+        assert stats["flip_frac"] < 1e-5 and stats["flip_max_rel_z"] < 1e-5, stats
 
 
 @pytest.mark.parametrize("case", C.CASES, ids=IDS)
