@@ -281,32 +281,56 @@ def extra_measurements(dev, hbm_gbs, peak_tf):
         rows.append({"mode": mode, "B": B, "ms": ms, "samples_per_s": B / ms * 1e3, "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / hbm_gbs})
         del ev
     out["head_only_fwd_bwd"] = {"bound": "hbm", "peak_GBps": hbm_gbs, "bytes_per_sample": HEAD_BYTES_PER_SAMPLE, "rows": rows}
-    # ---- HoME fusion path (cross' + 2 fuse' + image projection head + HOME_MMoE_Complete(768,4,2,512)), fwd+bwd bf16, B = 512
+    # ---- HoME micro-step (train_HoME.py:347-372): cross' + 2 fuse' + image projection head + 6 x HomeExpertWrapper + stack +
+    # HOME_MMoE_Complete(768,4,2,512) + two-task BCE + three InfoNCE terms, fwd+bwd bf16, B = 512.  Timed twice: with the
+    # script-side steps in torch (what the unchanged script does) and with the opt-in native versions (home_wrap / losses).
     B = 512
     cross, cui, cti = H.RobustTextCrossExpert().to(dev).train(), H.EnhancedCrossFuse().to(dev).train(), H.EnhancedCrossFuse().to(dev).train()
     hhead = H.HOME_MMoE_Complete(expert_dim=D, n_shared_experts=4, n_task_experts=2, tower_hidden=512).to(dev).train()
     img = H.ImageExpertWithProjection(Passthrough()).to(dev).train()
-    hm = [cross, cui, cti, hhead, img]
+    wraps = [pkg.home_wrap.HomeExpertWrapper(D).to(dev).train() for _ in range(6)]
+    fused_wraps = pkg.home_wrap.FusedHomeExpertStack(wraps)
+    bce = pkg.losses.TwoTaskBCEWithLogits()
+    hm = [cross, cui, cti, hhead, img] + wraps
     b = {k: v.to(dev) for k, v in make_host_batch(B, 5, pin=False).items()}
     u, i, ud, idoc = (b[k].requires_grad_(True) for k in ("u_sent", "i_sent", "u_doc", "i_doc"))
+    pw_g, pw_b = torch.tensor(POS_W_GOOD, device=dev), torch.tensor(POS_W_BEST, device=dev)
 
-    def home_step():
+    def torch_wrapper(w, x):                     # HomeExpertWrapper.forward, train_HoME.py:108-116
+        return w.dropout(F.silu(w.norm(x)))
+
+    def torch_nce(a, p, t=0.07):                 # calculate_contrastive_loss, train_HoME.py:43-51
+        sim = F.normalize(a, p=2, dim=1) @ F.normalize(p, p=2, dim=1).t() / t
+        return F.cross_entropy(sim, torch.arange(sim.size(0), device=sim.device))
+
+    def home_step(native_tail):
         for m in hm:
             m.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             img_vec, proj = img(b["img_tokens"])
             ui = cross(u, b["u_mask"], i, b["i_mask"])
             xui, xti = cui(ud, img_vec), cti(idoc, img_vec)
-            ev = torch.stack([ud, idoc, img_vec.float(), ui, xui, xti], 1)      # (HomeExpertWrapper BN is script-side)
-            lg, lb = hhead(ev)
-            loss = F.binary_cross_entropy_with_logits(lg.float(), b["y_good"]) + F.binary_cross_entropy_with_logits(lb.float(), b["y_best"]) + \
-                0.01 * proj.float().pow(2).mean()
+            six = [ud, idoc, img_vec.float(), ui, xui, xti]
+            if native_tail:
+                ev = fused_wraps(*six)
+                lg, lb = hhead(ev)
+                main = bce(lg, lb, b["y_good"], b["y_best"])
+                cl = pkg.losses.info_nce_losses([(ui, idoc), (ud, proj), (idoc, proj)]).sum()
+            else:
+                ev = torch.stack([torch_wrapper(w, x) for w, x in zip(wraps, six)], dim=1)
+                lg, lb = hhead(ev)
+                main = F.binary_cross_entropy_with_logits(lg.float(), b["y_good"], pos_weight=pw_g) + \
+                    F.binary_cross_entropy_with_logits(lb.float(), b["y_best"], pos_weight=pw_b)
+                cl = torch_nce(ui, idoc) + torch_nce(ud, proj) + torch_nce(idoc, proj)
+            loss = main + 0.1 * cl
         loss.backward()
-    ms = cuda_time(home_step, 3, 10)
-    tf = FLOP_PER_SAMPLE_HOME * B / (ms * 1e-3) / 1e12
-    out["home_path_fwd_bwd_bf16"] = {"B": B, "ms": ms, "samples_per_s": B / ms * 1e3, "path_tflops": tf, "path_frac_of_peak": tf / peak_tf,
-                                     "note": "single stream"}
-    del hm, cross, cui, cti, hhead, img
+    res = {}
+    for name, flag in (("script_side_torch", False), ("native_tail", True)):
+        ms = cuda_time(lambda: home_step(flag), 3, 10)
+        tf = FLOP_PER_SAMPLE_HOME * B / (ms * 1e-3) / 1e12
+        res[name] = {"ms": ms, "samples_per_s": B / ms * 1e3, "path_tflops": tf, "path_frac_of_peak": tf / peak_tf}
+    out["home_step_fwd_bwd_bf16"] = {"B": B, "note": "single stream; train_HoME.py:347-372 on one GPU (BASELINE configs[3] per-GPU work)", **res}
+    del hm, cross, cui, cti, hhead, img, wraps
     # ---- forward-only scoring (inference_and_auc.py:130-156), v1 path, no grad
     mods = build_modules(dev, train=False)
     rows = []

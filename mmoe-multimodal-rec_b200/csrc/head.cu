@@ -354,6 +354,8 @@ __global__ void __launch_bounds__(128, 2) head_fwd_reg_kernel(const HeadFusedDev
   const float inv_d = 1.f / (float)d, inv_n = 1.f / (float)NE;
   for (int64_t b = warp0; b < a.B; b += nw) {
     const float* evb = a.ev + b * (int64_t)NE * d;
+    // the warp's NEXT sample (18 KB) goes to L2 through one bulk request while this one is computed from registers
+    if (b + nw < a.B && lane == 0) prefetch_l2_bulk(a.ev + (b + nw) * (int64_t)NE * d, (uint32_t)(NE * d * 4));
     float4 E[NE][NV];
 #pragma unroll
     for (int k = 0; k < NE; ++k)
@@ -453,6 +455,11 @@ __global__ void __launch_bounds__(128, 2) head_bwd_reg_kernel(const HeadFusedDev
   const float inv_d = 1.f / (float)d, inv_n = 1.f / (float)NE;
   for (int64_t b = warp0; b < a.B; b += nw) {
     const float* evb = a.ev + b * (int64_t)NE * d;
+    if (b + nw < a.B) {
+      if (lane == 0) prefetch_l2_bulk(a.ev + (b + nw) * (int64_t)NE * d, (uint32_t)(NE * d * 4));
+      prefetch_l2_rows((const T*)a.dxn + (b + nw) * d, d * (int)sizeof(T), lane);
+      prefetch_l2_rows((const T*)a.dxn + ((int64_t)a.B + b + nw) * d, d * (int)sizeof(T), lane);
+    }
     float4 E[NE][NV];
 #pragma unroll
     for (int k = 0; k < NE; ++k)

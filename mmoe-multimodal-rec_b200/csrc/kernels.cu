@@ -172,6 +172,10 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const XT* __restrict__ x, c
   const float inv_d = 1.0f / (float)d;
   for (int64_t row = warp0; row < rows; row += nwarps) {
     const XT* xr = x + row * d;
+    if (row + nwarps < rows) {                 // this warp's next row: into L2 while this one is worked on
+      prefetch_l2_rows(x + (row + nwarps) * d, d * (int)sizeof(XT), lane);
+      if (delta != nullptr) prefetch_l2_rows(delta + (row + nwarps) * d, d * (int)sizeof(T), lane);
+    }
     float4 v[LN_NV];
     float sum = 0.f;
 #pragma unroll
@@ -353,6 +357,13 @@ __global__ void __launch_bounds__(128, 3) ln_bwd_kernel(const LnBwdDev a) {
   T* gout = reinterpret_cast<T*>(a.g_out);
   const bool want_wb = a.dgamma != nullptr, want_g = gout != nullptr || a.g_colsum != nullptr;
   for (int64_t row = warp0; row < a.rows; row += nwarps) {
+    if (row + nwarps < a.rows) {               // this warp's next row: into L2 while this one is worked on
+      const int64_t nx = (row + nwarps) * d;
+      prefetch_l2_rows(x + nx, d * (int)sizeof(XT), lane);
+      prefetch_l2_rows(dy + nx, d * (int)sizeof(DT_), lane);
+      if (a.dres != nullptr) prefetch_l2_rows(a.dres + nx, d * 4, lane);
+      if (a.dres_t != nullptr) prefetch_l2_rows(reinterpret_cast<const T*>(a.dres_t) + nx, d * (int)sizeof(T), lane);
+    }
     float4 xh[LN_NV], dg[LN_NV], rs[LN_NV];
 #pragma unroll
     for (int i = 0; i < LN_NV; ++i) {

@@ -31,6 +31,14 @@ def _is_gemm_weight(name: str, p: torch.Tensor, exclude=()) -> bool:
     return p.dim() == 2 and not any(name.endswith(e) or name == e for e in exclude)
 
 
+def _standalone(module, owner: str):
+    """Parameter containers that are evaluated inside their owner's fused launch sequence have no launch of their own: a
+    direct call fails loudly instead of dropping into torch eager (the package has no eager path)."""
+    raise NotImplementedError(
+        f"{type(module).__name__} holds parameters of {owner} and is executed inside that module's native kernels; the "
+        f"B200-native package has no stand-alone (torch eager) forward for it.  Call the owning module.")
+
+
 class _Native(nn.Module):
     """Shared plumbing: parameter pack in state_dict order + chunked no-grad execution."""
 
@@ -59,6 +67,9 @@ class AttnPool1D(nn.Module):
         super().__init__()
         self.query = nn.Parameter(torch.randn(1, 1, d) * (d ** -0.5))
         self.dropout = nn.Dropout(dropout)
+
+    def forward(self, x, mask):
+        _standalone(self, "RobustTextCrossExpert (fused gate-mix + pooling kernel)")
 
 
 class RobustTransformerLayer(nn.TransformerEncoderLayer):

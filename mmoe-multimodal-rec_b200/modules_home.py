@@ -12,8 +12,9 @@ from .modules import AttnPool1D, DenseGate, RobustTransformerLayer, _Native  # n
 
 
 def ExpertMLP(expert_dim: int, hidden_dim: int = 1024, dropout_p: float = 0.1):
-    """Parameter container of one HoME expert (reference model_HoME.py:28-35); the eight experts
-    are evaluated together by two grouped GEMM launches inside HOME_MMoE_Complete."""
+    """Parameter container of one HoME expert — a factory FUNCTION returning an nn.Sequential, exactly as in the reference
+    (model_HoME.py:28-35), so state-dict keys are 0.weight / 0.bias / 3.weight / 3.bias; the eight experts are evaluated
+    together by two grouped GEMM launches inside HOME_MMoE_Complete."""
     return nn.Sequential(nn.Linear(expert_dim, hidden_dim), nn.GELU(), nn.Dropout(dropout_p), nn.Linear(hidden_dim, expert_dim))
 
 
@@ -26,6 +27,9 @@ class FeatureGate(nn.Module):
         self.n_experts = n_experts
         self.d_model = d_model
 
+    def forward(self, x):
+        M._standalone(self, "HOME_MMoE_Complete (grouped gate GEMM + fg_apply kernel)")
+
 
 class SelfGate(nn.Module):
     """Container of a SelfGate (reference model_HoME.py:236-243): x + sigmoid(gate(x)) * y."""
@@ -33,6 +37,9 @@ class SelfGate(nn.Module):
     def __init__(self, d_model: int):
         super().__init__()
         self.gate = nn.Sequential(nn.Linear(d_model, d_model), nn.Sigmoid())
+
+    def forward(self, x_original, x_processed):
+        M._standalone(self, "HOME_MMoE_Complete (grouped gate GEMM + sg_apply kernel)")
 
 
 class RobustTextCrossExpert(M.RobustTextCrossExpert):
