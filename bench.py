@@ -125,16 +125,18 @@ class ClockSampler:
 
     def _loop(self):
         nv, h = self._nv, self._h
+        reasons = nv.nvmlDeviceGetCurrentClocksEventReasons if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)      # a constant: asked once
+        except Exception:
+            mx = 0
         while not self._stop.is_set():
             try:
-                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-                mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
-                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.samples.append((sm, mx, rs))
+                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), mx, reasons(h)))
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.025)
 
     def start(self):
         if self._h is None:
@@ -438,9 +440,11 @@ def main():
     if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
         torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)     # intentional: see step()
 
+    all_params = [p for m in mods for p in m.parameters()]
+
     def step(b):
-        for m in mods:
-            m.zero_grad(set_to_none=True)
+        for p in all_params:                 # what optimizer.zero_grad() does (train.py:288): walk a flat parameter list
+            p.grad = None
         ins = {k: (v.detach().requires_grad_(True) if k in grad_keys else v) for k, v in b.items()}
         cross_c, cui_c, cti_c, head_c = call["cross"], call["cui"], call["cti"], call["head"]
         with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -497,8 +501,8 @@ def main():
         step_ev[0].record()
         host_t = [time.perf_counter()]
         for i in range(n_steps):
-            if i >= 2 and not os.environ.get("BENCH_NO_THROTTLE"):
-                step_ev[i - 1].synchronize()   # stay at most two steps ahead of the device (bounded launch-queue depth)
+            if i >= 3 and not os.environ.get("BENCH_NO_THROTTLE"):
+                step_ev[i - 2].synchronize()   # stay at most three steps ahead of the device (bounded launch-queue depth)
             step(resident)
             step_ev[i + 1].record()
             host_t.append(time.perf_counter())
@@ -546,14 +550,18 @@ def main():
         exchange = "native flat-buffer all-reduce (functional.enable_grad_allreduce)"
 
     # ---------------- device-resident timing ----------------
+    # The NVML sampler starts BEFORE the warm-up steps: the first calls of each NVML query take tens of milliseconds and
+    # hold a driver lock that kernel launches also need (measured: with the sampler started right before the timed loop its
+    # second step took 18-110 ms of host time; started here, the first calls land in the warm-up).
+    sampler = ClockSampler(local_rank)
+    if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER"):
+        sampler.start()
     for _ in range(W):
         step(resident)
     barrier()
     L.mmoe_gemm_timing(128 * args.steps)           # event pairs for the roofline pass are created up front
     L.mmoe_gemm_timing(0)
-    sampler = ClockSampler(local_rank)
-    if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER"):
-        sampler.start()                            # first NVML calls happen during the extra warm-up step below
+    step(resident)
     step(resident)
     barrier()
     sampler.samples.clear()

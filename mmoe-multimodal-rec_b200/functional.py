@@ -90,20 +90,46 @@ class ParamPack:
         return out
 
 
+_LAYOUTS = {}
+
+
+def _grad_layout(params: Sequence[torch.Tensor], used: Sequence[bool]):
+    """(total floats, [(offset, shape, contiguous strides) or None]) of the flat gradient buffer; cached per shape signature."""
+    key = (tuple(tuple(p.shape) for p in params), tuple(bool(u) for u in used))
+    lay = _LAYOUTS.get(key)
+    if lay is None:
+        entries, off = [], 0
+        for p, u in zip(params, used):
+            if not u:
+                entries.append(None)
+                continue
+            shape = tuple(p.shape)
+            strides, acc = [], 1
+            for n in reversed(shape):
+                strides.append(acc)
+                acc *= n
+            entries.append((off, shape, tuple(reversed(strides))))
+            off += (p.numel() + 63) // 64 * 64
+        lay = (max(off, 1), entries)
+        _LAYOUTS[key] = lay
+    return lay
+
+
 def _alloc_grads(params: Sequence[torch.Tensor], used: Sequence[bool]):
-    """One zeroed fp32 buffer holding the gradients of all used parameters; returns (views, pointer list, flat buffer)."""
-    total = sum(p.numel() + 64 for p, u in zip(params, used) if u)
-    flat = torch.zeros(max(total, 1), dtype=torch.float32, device=params[0].device)
-    views, ptrs, off = [], [], 0
-    for p, u in zip(params, used):
-        if not u:
+    """One zeroed fp32 buffer holding the gradients of all used parameters (each at a 256-byte aligned offset); returns
+    (views, pointer list, flat buffer).  One as_strided per parameter: the view creation is host time on the critical
+    path of every backward (≈300 parameters per step)."""
+    total, entries = _grad_layout(params, used)
+    flat = torch.zeros(total, dtype=torch.float32, device=params[0].device)
+    base = flat.data_ptr()
+    views, ptrs = [], []
+    for e in entries:
+        if e is None:
             views.append(None)
             ptrs.append(None)
-            continue
-        v = flat[off:off + p.numel()].view(p.shape)
-        off += (p.numel() + 63) // 64 * 64
-        views.append(v)
-        ptrs.append(v.data_ptr())
+        else:
+            views.append(flat.as_strided(e[1], e[2], e[0]))
+            ptrs.append(base + 4 * e[0])
     return views, ptrs, flat
 
 
