@@ -10,7 +10,7 @@ import re
 import sys
 
 path = sys.argv[1]
-steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+steps = float(sys.argv[2]) if len(sys.argv) > 2 else 1
 with open(path) as f:
     lines = [l for l in f if not l.startswith("==")]
 tot, cnt = collections.defaultdict(float), collections.Counter()
