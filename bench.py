@@ -359,6 +359,79 @@ def extra_measurements(dev, hbm_gbs, peak_tf):
     return out
 
 
+def home_ddp_measurement(dev, local_rank, world, steps):
+    """BASELINE configs[3]: the HoME micro-step of train_HoME.py:347-404 on N GPUs, wrapped the way that script wraps it —
+    DistributedDataParallel(find_unused_parameters=True) around every module incl. the six HomeExpertWrapper instances
+    (train_HoME.py:190-202) — per-GPU batch 512, bf16 autocast, train mode.  Returns whole-job samples/s (max over ranks)."""
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    import mmoe_multimodal_rec_b200 as pkg
+    H = pkg.modules_home
+    B = 512
+    torch.manual_seed(4321)
+    raw = {"cross": H.RobustTextCrossExpert(), "cui": H.EnhancedCrossFuse(), "cti": H.EnhancedCrossFuse(),
+           "head": H.HOME_MMoE_Complete(expert_dim=D, n_shared_experts=4, n_task_experts=2, tower_hidden=512),
+           "img": H.ImageExpertWithProjection(Passthrough())}
+    class ScriptWrapper(torch.nn.Module):        # HomeExpertWrapper as train_HoME.py:100-116 defines it (script-side torch)
+        def __init__(self, d, p=0.1):
+            super().__init__()
+            self.norm, self.dropout = torch.nn.BatchNorm1d(d), torch.nn.Dropout(p)
+
+        def forward(self, x):
+            return self.dropout(F.silu(self.norm(x)))
+    for i in range(6):
+        raw[f"w{i}"] = ScriptWrapper(D)
+    mods = {k: DDP(m.to(dev).train(), device_ids=[local_rank], find_unused_parameters=True) for k, m in raw.items()}
+    params = [p for m in raw.values() for p in m.parameters()]
+    b = {k: v.to(dev) for k, v in make_host_batch(B, 4242 + local_rank, pin=False).items()}
+    u, i_, ud, idoc = (b[k].requires_grad_(True) for k in ("u_sent", "i_sent", "u_doc", "i_doc"))
+    pw_g, pw_b = torch.tensor(POS_W_GOOD, device=dev), torch.tensor(POS_W_BEST, device=dev)
+
+    def nce(a, p, t=0.07):                       # calculate_contrastive_loss, train_HoME.py:43-51
+        sim = F.normalize(a, p=2, dim=1) @ F.normalize(p, p=2, dim=1).t() / t
+        return F.cross_entropy(sim, torch.arange(sim.size(0), device=sim.device))
+
+    def step():
+        for p in params:
+            p.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            img_vec, proj = mods["img"](b["img_tokens"])
+            ui = mods["cross"](u, b["u_mask"], i_, b["i_mask"])
+            xui, xti = mods["cui"](ud, img_vec), mods["cti"](idoc, img_vec)
+            six = [ud, idoc, img_vec.float(), ui, xui, xti]
+            ev = torch.stack([mods[f"w{k}"](x) for k, x in enumerate(six)], dim=1)           # train_HoME.py:350-356
+            lg, lb = mods["head"](ev)
+            loss = F.binary_cross_entropy_with_logits(lg.float(), b["y_good"], pos_weight=pw_g) + \
+                F.binary_cross_entropy_with_logits(lb.float(), b["y_best"], pos_weight=pw_b) + \
+                0.1 * (nce(ui, idoc) + nce(ud, proj) + nce(idoc, proj))
+        loss.backward()
+    for _ in range(4):
+        step()
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {"B_per_gpu": B, "ms_per_step": ms, "samples_per_s": B * world / (ms * 1e-3), "steps": steps,
+            "wrapping": "13 DistributedDataParallel(find_unused_parameters=True) wrappers, script-side BN wrappers / InfoNCE in torch"}
+
+
+def small_batch_measurement(dev, step_factory, B_small, ms_per_sample_ref):
+    """The README configuration (2 GPUs x batch 128, README.md:253-263): the same step at B = 128 per GPU.  At this size the
+    step is launch-latency bound (≈180 launches), so its per-sample cost against the B = 512 line shows what launch overhead
+    costs."""
+    step = step_factory(B_small)
+    ms = cuda_time(step, 5, 20)
+    return {"B": B_small, "ms_per_step": ms, "samples_per_s": B_small / ms * 1e3,
+            "per_sample_cost_vs_b512": (ms / B_small) / ms_per_sample_ref}
+
+
 # ----------------------------------------------------------------------------------------------
 _REAL_STDOUT = None
 
@@ -655,6 +728,12 @@ def main():
     e2e_value = B * world / (max_over_ranks(e_ms) / args.steps * 1e-3)
     gc.enable()
 
+    home_ddp = None
+    if distributed and not args.no_extras:
+        try:
+            home_ddp = home_ddp_measurement(dev, local_rank, world, 10)
+        except Exception as ex:  # noqa: BLE001
+            home_ddp = {"error": repr(ex)}
     if rank == 0:
         peaks = {}
         try:
@@ -727,6 +806,8 @@ def main():
         }
         if native_result is not None:
             line["native_exchange"] = native_result
+        if home_ddp is not None:
+            line["extra"] = {"home_step_ddp_fwd_bwd_bf16": home_ddp}
         if world == 1 and not args.no_extras:
             # ---- the same step in eager PyTorch on this GPU (torch's own kernels), same weights ----
             try:
@@ -749,6 +830,11 @@ def main():
                 line["eager_b200"] = {"error": repr(ex)}
             try:
                 line["extra"] = extra_measurements(dev, hbm, peak_tf)
+
+                def factory(Bs):
+                    bs = {k: v.to(dev) for k, v in make_host_batch(Bs, 77, pin=False).items()}
+                    return lambda: step(bs)
+                line["extra"]["v1_step_b128"] = small_batch_measurement(dev, factory, 128, ms_step / B)
             except Exception as ex:  # noqa: BLE001
                 line["extra"] = {"error": repr(ex)}
         if not args.no_cpu_baseline and world == 1:
