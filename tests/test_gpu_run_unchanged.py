@@ -18,11 +18,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _have(script):
-    fname = script + ".py"
+    fname = script if script == "infer_auc_HoME" else script + ".py"
     return any(os.path.isfile(os.path.join(d, fname)) for d in ("/root/reference", os.path.join(ROOT, "baseline", "_ref")))
 
 
-@pytest.mark.parametrize("script", ["train", "train_HoME", "inference_and_auc"])
+@pytest.mark.parametrize("script", ["train", "train_HoME", "inference_and_auc", "infer_auc_HoME"])
 def test_reference_script_runs_unchanged_on_the_dropins(script):
     if not _have(script):
         pytest.skip("reference scripts not staged (run __graft_entry__.build() in the dev container)")
@@ -38,3 +38,5 @@ def test_reference_script_runs_unchanged_on_the_dropins(script):
         assert r.stdout.count("Total Loss") >= 2, tail
     if script == "inference_and_auc":
         assert "AUC for 'good' task" in r.stdout and "AUC for 'best' task" in r.stdout, tail
+    if script == "infer_auc_HoME":             # fp32 (no autocast), BN wrappers from the reference's train_HoME.py, pandas CSV
+        assert "AUC(good)" in r.stdout and "AUC(best)" in r.stdout and "Saved predictions" in r.stdout, tail

@@ -195,7 +195,8 @@ def load_script(name: str):
     mod = importlib.util.module_from_spec(spec)
     sys.modules[loader.name] = mod
     if name == "infer_auc_HoME":
-        sys.modules.setdefault("train_HoME", load_script("train_HoME"))
+        if "train_HoME" not in sys.modules:          # `from train_HoME import HomeExpertWrapper` (infer_auc_HoME:139)
+            sys.modules["train_HoME"] = load_script("train_HoME")[0]
     loader.exec_module(mod)
     return mod, path
 
@@ -211,9 +212,22 @@ def make_checkpoint(path: str, device):
     torch.save({k: m.state_dict() for k, m in mods.items()} | {"epoch": 0}, path)
 
 
+def make_home_checkpoint(path: str, device, wrapper_cls):
+    """A checkpoint with the keys train_HoME.py:432-451 writes (modules + the six BN wrappers), random init."""
+    import model_HoME as M
+    tok = FakeTokenizer(); tok.add_tokens(["<SENT>"])
+    mods = {"user": M.build_text_user_expert("x", 8, 384, tok, device), "item": M.build_text_item_expert("x", 8, 384, tok, device),
+            "img": M.build_img_expert("x", device=device), "cross_ui": M.build_cross_expert(device=device),
+            "concat_ui": M.build_concat_ui_expert(device=device), "concat_ti": M.build_concat_ti_expert(device=device),
+            "head": M.HOME_MMoE_Complete(expert_dim=768, n_shared_experts=4, n_task_experts=2, tower_hidden=512).to(device)}
+    for k in ("u_doc_wrapper", "i_doc_wrapper", "img_vec_wrapper", "ui_vec_wrapper", "xui_wrapper", "xti_wrapper"):
+        mods[k] = wrapper_cls(d_model=768).to(device)
+    torch.save({k: m.state_dict() for k, m in mods.items()} | {"epoch": 0}, path)
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("script", choices=["train", "train_HoME", "inference_and_auc"])
+    ap.add_argument("script", choices=["train", "train_HoME", "inference_and_auc", "infer_auc_HoME"])
     ap.add_argument("--batches", type=int, default=4)
     ap.add_argument("--batch-size", type=int, default=8)
     ap.add_argument("--grad-accum", type=int, default=2)
@@ -222,7 +236,7 @@ def main():
     work = tempfile.mkdtemp(prefix="mmoe_ref_run_")
     open(os.path.join(work, "shard-000000.tar"), "wb").close()
     FakeWebDataset.limit_batches = a.batches
-    FakeWebDataset.endless = a.script != "inference_and_auc"
+    FakeWebDataset.endless = a.script in ("train", "train_HoME")
     mod, path = load_script(a.script)
     argv = [path, "--data_pattern", os.path.join(work, "shard-*.tar"), "--batch_size", str(a.batch_size), "--num_workers", "0",
             "--output_dir", os.path.join(work, "out")]
@@ -230,6 +244,10 @@ def main():
         ckpt = os.path.join(work, "ckpt.pt")
         make_checkpoint(ckpt, torch.device("cuda"))
         argv += ["--checkpoint_path", ckpt]
+    elif a.script == "infer_auc_HoME":
+        ckpt = os.path.join(work, "ckpt_home.pt")
+        make_home_checkpoint(ckpt, torch.device("cuda"), sys.modules["train_HoME"].HomeExpertWrapper)
+        argv += ["--ckpt", ckpt]
     else:
         argv += ["--grad_accum", str(a.grad_accum), "--epochs", "1"]
     sys.argv = argv
