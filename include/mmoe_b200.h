@@ -87,9 +87,12 @@ typedef struct {
   float        alpha;
   float        drop_p;      /* dropout after the activation / backward multiplier           */
   uint32_t     drop_key0, drop_key1;   /* mask(m,n) = f(key, m*N + n), see mmoe_dropout_mask */
-  void*        mask_out;    /* uint64 [M, N/64] or NULL: bit n%64 of word [m, n/64] = (stored value != 0).
-                               Lets the ReLU(+dropout) backward read 1 bit per element instead of the saved
-                               activation.  16-bit tensor-core path only (N % 64 == 0); fails loudly otherwise. */
+  void*        mask_out;    /* uint64 [M, N/64] or NULL: one flag per element = (stored 16-bit value != 0), for the columns
+                               64w .. 64w+63 of row m in word [m, w].  Flag of column 64w + c:  bit  32*(c/32) + (c odd ?
+                               31 : 15) - (c%32)/2  (the order the epilogue's packed 16-bit pairs produce with 3 integer
+                               operations per pair).  Lets the ReLU(+dropout) backward read 1 bit per element instead of
+                               the saved activation; consumed by bwd_mode 4.  16-bit tensor-core path only (N % 64 == 0,
+                               act == ReLU); fails loudly otherwise. */
 } mmoe_epilogue;
 
 typedef struct {

@@ -423,12 +423,11 @@ __device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int tile) {
 //   SCALED: the bias table already holds bias * dscale and the dropout scale is folded into one FFMA (act <= 1 only)
 //   DROP  : keyed-hash dropout; the pair index fits 32 bits (checked on the host), so the high-word term of drop_hash
 //           vanishes and the key mix is hoisted; keep tests are done on the raw 32-bit hash (no field extraction)
-//   MASK  : also returns bit j = (value j != 0) for the 64 values (the ReLU / dropout pattern, for mask_out)
+//   MASK  : also returns the 64 non-zero flags of the stored values (the ReLU / dropout pattern, for mask_out; layout below)
 template <int ACT, bool DROP, bool SCALED, bool BF16, bool MASK = false>
 __device__ __forceinline__ uint64_t epi_chunk_math(const uint32_t (&v)[64], const float* tab, uint32_t (&pk)[32], float dscale,
                                                    uint32_t thresh, uint32_t dk0, uint32_t dk1, uint32_t pair0) {
   const uint32_t thi = thresh << 16;
-  uint32_t bits_lo = 0u, bits_hi = 0u;
 #pragma unroll
   for (int j = 0; j < 64; j += 2) {
     const float2 bb = *reinterpret_cast<const float2*>(tab + j);           // warp-uniform address: smem broadcast
@@ -448,12 +447,22 @@ __device__ __forceinline__ uint64_t epi_chunk_math(const uint32_t (&v)[64], cons
       else { v0 = k0 ? v0 * dscale : 0.f; v1 = k1 ? v1 * dscale : 0.f; }
     }
     pk[j >> 1] = BF16 ? pack_bf16(v0, v1) : pack_f16(v0, v1);
-    if (MASK) {
-      const uint32_t b2 = (v0 != 0.f ? 1u : 0u) | (v1 != 0.f ? 2u : 0u);
-      if (j < 32) bits_lo |= b2 << (j & 31); else bits_hi |= b2 << (j & 31);
-    }
   }
-  return ((uint64_t)bits_hi << 32) | bits_lo;
+  if (MASK) {
+    // Non-zero flags of the 64 STORED 16-bit values, from the packed words (3 integer ops per pair instead of two float
+    // compares, selects and shifts per element).  The values are >= 0 (ReLU, then dropout), so adding 0x7FFF to a half sets
+    // its top bit iff the half is non-zero, without a carry into the other half.  Bit layout of the 64-bit mask word
+    // (mmoe_epilogue.mask_out): low 32 bits = packed words 0..15, high 32 bits = words 16..31; inside each, bit 15 - i
+    // flags the low half (even column) of word i and bit 31 - i its high half (odd column).
+    uint32_t lo = 0u, hi = 0u;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      lo |= ((pk[i] + 0x7FFF7FFFu) >> i) & (0x80008000u >> i);
+      hi |= ((pk[16 + i] + 0x7FFF7FFFu) >> i) & (0x80008000u >> i);
+    }
+    return ((uint64_t)hi << 32) | lo;
+  }
+  return 0ull;
 }
 template <bool RICH, bool BF16>
 __device__ __forceinline__ uint64_t epi_chunk_dispatch(int act, bool drop, bool scaled, bool want_mask, const uint32_t (&v)[64],
@@ -790,11 +799,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           else outbits = epi_chunk_dispatch<RICH, false>(act, drop, scaled, mask_out != nullptr, v, tab, pk, dscale, thresh, dk0, dk1, pair0);
           if (RICH && mask_out != nullptr && m < g.M) mask_out[m * words + (nb >> 6)] = outbits;
           if (bitmode) {
-            // keep the 16-bit halves whose bit is set (rows >= M carry inbits = 0 and contribute nothing to the column sums)
+            // keep the 16-bit halves whose flag is set (layout: see epi_chunk_math; rows >= M carry inbits = 0 and contribute
+            // nothing to the column sums)
+            const uint32_t blo = (uint32_t)inbits, bhi = (uint32_t)(inbits >> 32);
 #pragma unroll
-            for (int w = 0; w < 32; ++w) {
-              const uint32_t b2 = (uint32_t)(inbits >> (2 * w)) & 3u;
-              pk[w] &= ((b2 & 1u) * 0xFFFFu) | ((b2 >> 1) * 0xFFFF0000u);
+            for (int i = 0; i < 16; ++i) {
+              pk[i] &= (((blo << i) & 0x80008000u) >> 15) * 0xFFFFu;
+              pk[16 + i] &= (((bhi << i) & 0x80008000u) >> 15) * 0xFFFFu;
             }
           }
           if (store_pending) {                   // the previous TMA store must have finished reading the slab
