@@ -219,22 +219,27 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const __grid_constant__ 
 // ------------------------------------------------------------------------------------------
 constexpr int TBM = 128, TBN = 256, TBK = 64;
 constexpr int TA_BYTES = TBM * TBK * 2;   // 16 KB
-// One CTA per tile: 4 stages of {A 128x64, B 256x64} = 4 x 48 KB.  CTA pair (cta_group::2) on a 256 x 256 tile: each CTA
-// stages its own 128 rows of A and HALF of B (128 x 64), 6 stages of 32 KB — the same 192 KB, but a third less
-// L2 -> shared-memory traffic per FLOP, which is what bounds the one-CTA kernel on the large GEMMs.
-template <int CTAS> struct TcCfg {
-  static constexpr int STAGES = CTAS == 2 ? 6 : 4;
-  static constexpr int B_BYTES = (TBN / CTAS) * TBK * 2;
+// One CTA per tile: stages of {A 128x64, B BNx64}.  CTA pair (cta_group::2) on a 256 x 256 tile: each CTA stages its own
+// 128 rows of A and HALF of B (128 x 64), 6 stages of 32 KB — a third less L2 -> shared-memory traffic per FLOP than one
+// CTA per tile, which is what bounds the one-CTA kernel on the large GEMMs.  The ring always fills the same 192 KB: the
+// narrow tiles of the small-batch problems (fuse experts, heads: one or two tiles per CTA, 12-48 K-blocks each) get a
+// DEEPER ring instead of a smaller one — with one tile per CTA there is no tile-level overlap, so the K loop runs at
+// TMA latency / ring depth per K-block (4 stages: ~0.25 us per K-block, 26 us for a 48-K-block tile at B = 128).
+template <int BN, int CTAS> struct TcCfg {
+  static constexpr int B_BYTES = (BN / CTAS) * TBK * 2;
   static constexpr int STAGE_BYTES = TA_BYTES + B_BYTES;
+  static constexpr int STAGES = CTAS == 2 ? 6 : (BN == 64 ? 8 : (BN == 128 ? 6 : 4));
 };
 constexpr int TC_PIPE_BYTES = 4 * (TA_BYTES + TBN * TBK * 2);
-static_assert(TcCfg<1>::STAGES * TcCfg<1>::STAGE_BYTES == TC_PIPE_BYTES && TcCfg<2>::STAGES * TcCfg<2>::STAGE_BYTES == TC_PIPE_BYTES, "pipeline bytes");
-constexpr int TMAX_STAGES = 6;
+static_assert(TcCfg<256, 1>::STAGES * TcCfg<256, 1>::STAGE_BYTES == TC_PIPE_BYTES && TcCfg<256, 2>::STAGES * TcCfg<256, 2>::STAGE_BYTES == TC_PIPE_BYTES &&
+              TcCfg<128, 1>::STAGES * TcCfg<128, 1>::STAGE_BYTES == TC_PIPE_BYTES && TcCfg<64, 1>::STAGES * TcCfg<64, 1>::STAGE_BYTES == TC_PIPE_BYTES,
+              "pipeline bytes");
+constexpr int TMAX_STAGES = 8;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TEPI_WARP_BYTES = 4096;     // per-warp staging slab: 32 rows x 128 B
 constexpr int TEPI_BYTES = TC_EPI_WARPS * TEPI_WARP_BYTES;
 constexpr int TEPI_BIAS_BYTES = TC_EPI_WARPS * 64 * 4;   // per epilogue warp: the 64 bias values of its current chunk (fast epilogue)
-constexpr int TBAR_BYTES = 256;              // 16 mbarriers + the TMEM base slot
+constexpr int TBAR_BYTES = 256;              // 20 mbarriers + the TMEM base slot + the tile-scheduler ring
 constexpr int TC_SMEM_BYTES = TC_PIPE_BYTES + TEPI_BYTES + TBAR_BYTES + TEPI_BIAS_BYTES;   // 231,680 B of the 232,448 B limit
 constexpr int TC_THREADS = 128 + 32 * TC_EPI_WARPS;
 
@@ -500,7 +505,7 @@ __device__ __forceinline__ uint64_t epi_chunk_dispatch(int act, bool drop, bool 
 // only the leader issues MMAs.
 template <int BN, bool RICH, int CTAS>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
-  constexpr int TSTAGES = TcCfg<CTAS>::STAGES, TB_BYTES = TcCfg<CTAS>::B_BYTES, TSTAGE_BYTES = TcCfg<CTAS>::STAGE_BYTES;
+  constexpr int TSTAGES = TcCfg<BN, CTAS>::STAGES, TB_BYTES = TcCfg<BN, CTAS>::B_BYTES, TSTAGE_BYTES = TcCfg<BN, CTAS>::STAGE_BYTES;
   constexpr int BN_CTA = BN / CTAS;                      // B rows this CTA stages
   const uint32_t crank = CTAS == 2 ? cluster_rank() : 0u;
   const int first_tile = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -515,7 +520,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   const uint32_t smem_b0 = smem_base + TSTAGES * TA_BYTES;
   float* epi_stage = reinterpret_cast<float*>(smem_gen + TSTAGES * TSTAGE_BYTES);
   const uint32_t bar_base = smem_base + TSTAGES * TSTAGE_BYTES + TEPI_BYTES;
-  // barrier layout: full[6], empty[6], tmem_full[2], tmem_empty[2] (16 x 8 B), then the TMEM base slot
+  // barrier layout: full[8], empty[8], tmem_full[2], tmem_empty[2] (20 x 8 B), then the TMEM base slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (TMAX_STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * TMAX_STAGES + s); };
@@ -530,7 +535,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   // other role reads it from there.  A CTA that cannot be scheduled at once (an SM held by a communication kernel) then
   // simply draws fewer tiles, instead of leaving its statically assigned share for a second wave.
   const bool dyn = p.tile_counter != nullptr;
-  const uint32_t sched_base = bar_base + 144u;
+  const uint32_t sched_base = bar_base + 8u * (2 * TMAX_STAGES + 4) + 16u;
   auto tilefull_bar = [&](int s) { return sched_base + 8u * s; };
   auto tileempty_bar = [&](int s) { return sched_base + 16u + 8u * s; };
   auto ring_addr = [&](int s) { return sched_base + 32u + 4u * s; };
