@@ -346,45 +346,37 @@ template <> __device__ __forceinline__ float4 ld4_as<__half>(const __half* p) {
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 __device__ __forceinline__ void fma4(float4& acc, float s, float4 v) { acc.x = fmaf(s, v.x, acc.x); acc.y = fmaf(s, v.y, acc.y); acc.z = fmaf(s, v.z, acc.z); acc.w = fmaf(s, v.w, acc.w); }
 
-// One warp per sample.  Round 1 kept the whole sample (6 x 768 fp32 = 144 registers per lane) in registers: 255 registers,
-// 8 warps per SM, and the warps sat on their own loads (ncu: DRAM 40 %, long-scoreboard stalls).  Now the sample is read
-// TWICE — once for the mean query (24 accumulator registers), once for the two gate-weighted sums (48) — the second
-// read coming from L1/L2 (the warp's next sample is bulk-prefetched into L2 while this one is computed), which halves
-// the registers and doubles the resident warps.
 template <typename T, int NE, int NV>
-__global__ void __launch_bounds__(128, 4) head_fwd_reg_kernel(const HeadFusedDev a) {
+__global__ void __launch_bounds__(128, 2) head_fwd_reg_kernel(const HeadFusedDev a) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int d = a.d;
   const float inv_d = 1.f / (float)d, inv_n = 1.f / (float)NE;
   for (int64_t b = warp0; b < a.B; b += nw) {
     const float* evb = a.ev + b * (int64_t)NE * d;
+    // the warp's NEXT sample (18 KB) goes to L2 through one bulk request while this one is computed from registers
     if (b + nw < a.B && lane == 0) prefetch_l2_bulk(a.ev + (b + nw) * (int64_t)NE * d, (uint32_t)(NE * d * 4));
-    // ---- pass 1: mean query
-    float4 q[NV];
+    float4 E[NE][NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) q[i] = make_float4(0, 0, 0, 0);
-#pragma unroll
-    for (int k = 0; k < NE; ++k) {
-      float4 e[NV];
+    for (int k = 0; k < NE; ++k)
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int c = (i * 32 + lane) * 4;
-        e[i] = c < d ? __ldg(reinterpret_cast<const float4*>(evb + k * d + c)) : make_float4(0, 0, 0, 0);
+        E[k][i] = c < d ? __ldcs(reinterpret_cast<const float4*>(evb + k * d + c)) : make_float4(0, 0, 0, 0);
       }
-#pragma unroll
-      for (int i = 0; i < NV; ++i) { q[i].x += e[i].x; q[i].y += e[i].y; q[i].z += e[i].z; q[i].w += e[i].w; }
-    }
+    float4 q[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
+      q[i] = E[0][i];
+#pragma unroll
+      for (int k = 1; k < NE; ++k) { q[i].x += E[k][i].x; q[i].y += E[k][i].y; q[i].z += E[k][i].z; q[i].w += E[k][i].w; }
       q[i].x *= inv_n; q[i].y *= inv_n; q[i].z *= inv_n; q[i].w *= inv_n;
       const int c = (i * 32 + lane) * 4;
       if (c < d) st4_as<T>((T*)a.query_t + b * d + c, q[i]);
     }
-    // ---- both gates: 2 x NE dot products with the query, softmax
-    float wk[2][NE];
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
+      float wk[NE];
 #pragma unroll
       for (int k = 0; k < NE; ++k) {
         float acc = 0.f;
@@ -393,62 +385,42 @@ __global__ void __launch_bounds__(128, 4) head_fwd_reg_kernel(const HeadFusedDev
           const int c = (i * 32 + lane) * 4;
           if (c < d) acc += dot4(q[i], __ldg(reinterpret_cast<const float4*>(a.wg[t] + k * d + c)));
         }
-        wk[t][k] = acc;
+        wk[k] = acc;
       }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
+      for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-      for (int t = 0; t < 2; ++t)
-#pragma unroll
-        for (int k = 0; k < NE; ++k) wk[t][k] += __shfl_xor_sync(0xffffffffu, wk[t][k], o);
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
+        for (int k = 0; k < NE; ++k) wk[k] += __shfl_xor_sync(0xffffffffu, wk[k], o);
       float m = -INFINITY;
 #pragma unroll
-      for (int k = 0; k < NE; ++k) { wk[t][k] += a.bg[t][k]; m = fmaxf(m, wk[t][k]); }
+      for (int k = 0; k < NE; ++k) { wk[k] += a.bg[t][k]; m = fmaxf(m, wk[k]); }
       float ssum = 0.f;
 #pragma unroll
-      for (int k = 0; k < NE; ++k) { wk[t][k] = expf(wk[t][k] - m); ssum += wk[t][k]; }
+      for (int k = 0; k < NE; ++k) { wk[k] = expf(wk[k] - m); ssum += wk[k]; }
       const float inv = 1.f / ssum;
 #pragma unroll
-      for (int k = 0; k < NE; ++k) wk[t][k] *= inv;
+      for (int k = 0; k < NE; ++k) wk[k] *= inv;
       if (lane < NE) {
-        float mine = wk[t][0];
+        float mine = wk[0];
 #pragma unroll
-        for (int k = 1; k < NE; ++k) mine = lane == k ? wk[t][k] : mine;
+        for (int k = 1; k < NE; ++k) mine = lane == k ? wk[k] : mine;
         a.w[((int64_t)t * a.B + b) * NE + lane] = mine;
       }
-    }
-    // ---- pass 2: both gate-weighted sums from one more read of the sample (L1 / L2)
-    float4 f[2][NV];
-#pragma unroll
-    for (int t = 0; t < 2; ++t)
-#pragma unroll
-      for (int i = 0; i < NV; ++i) f[t][i] = make_float4(0, 0, 0, 0);
-#pragma unroll
-    for (int k = 0; k < NE; ++k) {
-      float4 e[NV];
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c = (i * 32 + lane) * 4;
-        e[i] = c < d ? __ldg(reinterpret_cast<const float4*>(evb + k * d + c)) : make_float4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int i = 0; i < NV; ++i) { fma4(f[0][i], wk[0][k], e[i]); fma4(f[1][i], wk[1][k], e[i]); }
-    }
-    // ---- tower LayerNorms
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
+      float4 f[NV];
       float sum = 0.f;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) sum += f[t][i].x + f[t][i].y + f[t][i].z + f[t][i].w;
+      for (int i = 0; i < NV; ++i) {
+        f[i] = make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < NE; ++k) fma4(f[i], wk[k], E[k][i]);
+        sum += f[i].x + f[i].y + f[i].z + f[i].w;
+      }
       const float mean = warp_sum(sum) * inv_d;
       float sq = 0.f;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int c = (i * 32 + lane) * 4;
-        if (c < d) { const float x0 = f[t][i].x - mean, x1 = f[t][i].y - mean, x2 = f[t][i].z - mean, x3 = f[t][i].w - mean; sq += x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3; }
+        if (c < d) { const float x0 = f[i].x - mean, x1 = f[i].y - mean, x2 = f[i].z - mean, x3 = f[i].w - mean; sq += x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3; }
       }
       const float rstd = rsqrtf(warp_sum(sq) * inv_d + 1e-5f);
       if (lane == 0) { a.stats[((int64_t)t * a.B + b) * 2] = mean; a.stats[((int64_t)t * a.B + b) * 2 + 1] = rstd; }
@@ -458,8 +430,8 @@ __global__ void __launch_bounds__(128, 4) head_fwd_reg_kernel(const HeadFusedDev
         const int c = (i * 32 + lane) * 4;
         if (c < d) {
           const float4 g = __ldg(reinterpret_cast<const float4*>(a.ln_w[t] + c)), be = __ldg(reinterpret_cast<const float4*>(a.ln_b[t] + c));
-          st4_as<T>(xo + c, make_float4((f[t][i].x - mean) * rstd * g.x + be.x, (f[t][i].y - mean) * rstd * g.y + be.y,
-                                        (f[t][i].z - mean) * rstd * g.z + be.z, (f[t][i].w - mean) * rstd * g.w + be.w));
+          st4_as<T>(xo + c, make_float4((f[i].x - mean) * rstd * g.x + be.x, (f[i].y - mean) * rstd * g.y + be.y,
+                                        (f[i].z - mean) * rstd * g.z + be.z, (f[i].w - mean) * rstd * g.w + be.w));
         }
       }
     }
@@ -468,7 +440,7 @@ __global__ void __launch_bounds__(128, 4) head_fwd_reg_kernel(const HeadFusedDev
 
 // dynamic smem: per warp [2 tasks][dgamma | dbeta][NV*128] fp32 partial sums (warp-private columns: no atomics)
 template <typename T, int NE, int NV>
-__global__ void __launch_bounds__(128, 4) head_bwd_reg_kernel(const HeadFusedDev a) {
+__global__ void __launch_bounds__(128, 2) head_bwd_reg_kernel(const HeadFusedDev a) {
   constexpr int WARPS = 4, COLS = NV * 128;
   extern __shared__ float4 acc_sm4[];
   float* acc_sm = reinterpret_cast<float*>(acc_sm4);
@@ -488,31 +460,20 @@ __global__ void __launch_bounds__(128, 4) head_bwd_reg_kernel(const HeadFusedDev
       prefetch_l2_rows((const T*)a.dxn + (b + nw) * d, d * (int)sizeof(T), lane);
       prefetch_l2_rows((const T*)a.dxn + ((int64_t)a.B + b + nw) * d, d * (int)sizeof(T), lane);
     }
-    // Two reads of the sample instead of 144 resident registers (see head_fwd_reg_kernel): pass 1 rebuilds both gate-weighted
-    // sums, pass 2 (from L1 / L2) takes the 2 x NE dot products of the gate backward.
-    float wt[2][NE];
+    float4 E[NE][NV];
 #pragma unroll
-    for (int t = 0; t < 2; ++t)
-#pragma unroll
-      for (int k = 0; k < NE; ++k) wt[t][k] = a.w[((int64_t)t * a.B + b) * NE + k];
-    float4 df[2][NV];
-#pragma unroll
-    for (int t = 0; t < 2; ++t)
-#pragma unroll
-      for (int i = 0; i < NV; ++i) df[t][i] = make_float4(0, 0, 0, 0);
-#pragma unroll
-    for (int k = 0; k < NE; ++k) {
-      float4 e[NV];
+    for (int k = 0; k < NE; ++k)
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int c = (i * 32 + lane) * 4;
-        e[i] = c < d ? __ldg(reinterpret_cast<const float4*>(evb + k * d + c)) : make_float4(0, 0, 0, 0);
+        E[k][i] = c < d ? __ldcs(reinterpret_cast<const float4*>(evb + k * d + c)) : make_float4(0, 0, 0, 0);
       }
-#pragma unroll
-      for (int i = 0; i < NV; ++i) { fma4(df[0][i], wt[0][k], e[i]); fma4(df[1][i], wt[1][k], e[i]); }
-    }
+    float wt[2][NE];
+    float4 df[2][NV];
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
+#pragma unroll
+      for (int k = 0; k < NE; ++k) wt[t][k] = a.w[((int64_t)t * a.B + b) * NE + k];
       const float mean = a.stats[((int64_t)t * a.B + b) * 2], rstd = a.stats[((int64_t)t * a.B + b) * 2 + 1];
       const T* dy = (const T*)a.dxn + ((int64_t)t * a.B + b) * d;
       float4 dg[NV];
@@ -520,7 +481,9 @@ __global__ void __launch_bounds__(128, 4) head_bwd_reg_kernel(const HeadFusedDev
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int c = (i * 32 + lane) * 4;
-        const float4 f = df[t][i];                 // the gate-weighted sum; replaced by xhat, then by d fused
+        float4 f = make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < NE; ++k) fma4(f, wt[t][k], E[k][i]);
         dg[i] = make_float4(0, 0, 0, 0);
         df[t][i] = make_float4(0, 0, 0, 0);
         if (c < d) {
@@ -551,21 +514,17 @@ __global__ void __launch_bounds__(128, 4) head_bwd_reg_kernel(const HeadFusedDev
         }
       }
     }
-    // gate backward: dw_t[k] = <dfused_t, E_k>  (12 dot products reduced together), second read of the sample
+    // gate backward: dw_t[k] = <dfused_t, E_k>  (12 dot products reduced together)
     float dw[2][NE];
 #pragma unroll
-    for (int k = 0; k < NE; ++k) {
-      float4 e[NV];
+    for (int t = 0; t < 2; ++t)
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c = (i * 32 + lane) * 4;
-        e[i] = c < d ? __ldg(reinterpret_cast<const float4*>(evb + k * d + c)) : make_float4(0, 0, 0, 0);
+      for (int k = 0; k < NE; ++k) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc += dot4(df[t][i], E[k][i]);
+        dw[t][k] = acc;
       }
-      float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) { a0 += dot4(df[0][i], e[i]); a1 += dot4(df[1][i], e[i]); }
-      dw[0][k] = a0; dw[1][k] = a1;
-    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
@@ -675,7 +634,7 @@ static int head_fwd_t(const mmoe_call* c, const mmoe_head_cfg* cfg, const float*
     HeadFusedDev a = head_dev<T>(c, cfg, ev, s, ix);
     if (n == 6 && d <= 768) {
       int64_t blocks = ((int64_t)B + 3) / 4;
-      if (blocks > (int64_t)sm_count() * 4) blocks = (int64_t)sm_count() * 4;
+      if (blocks > (int64_t)sm_count() * 2) blocks = (int64_t)sm_count() * 2;
       head_fwd_reg_kernel<T, 6, 6><<<(int)blocks, 128, 0, st>>>(a);
     } else if (d <= 768) head_mix_ln_fwd_kernel<T, 6><<<rows_grid(B, 8), 256, 0, st>>>(a);
     else head_mix_ln_fwd_kernel<T, 8><<<rows_grid(B, 8), 256, 0, st>>>(a);
@@ -777,7 +736,7 @@ static int head_bwd_t(const mmoe_call* c, const mmoe_head_cfg* cfg, const float*
         MMOE_CUDA(cudaFuncSetAttribute(head_bwd_reg_kernel<T, 6, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BYTES));
         attr = true;
       }
-      if (blocks > (int64_t)sm_count() * 4) blocks = (int64_t)sm_count() * 4;
+      if (blocks > (int64_t)sm_count() * 2) blocks = (int64_t)sm_count() * 2;
       head_bwd_reg_kernel<T, 6, 6><<<(int)blocks, 128, SM_BYTES, st>>>(a);
     } else if (d <= 768) head_ln_mix_bwd_kernel<T, 6><<<(int)blocks, 128, 0, st>>>(a);
     else head_ln_mix_bwd_kernel<T, 8><<<(int)blocks, 128, 0, st>>>(a);
