@@ -6,6 +6,18 @@
 
 namespace mmoe {
 
+template <typename TT> __device__ __forceinline__ float4 img_ld4(const TT* p);
+template <> __device__ __forceinline__ float4 img_ld4<float>(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+template <> __device__ __forceinline__ float4 img_ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 u = __ldcs(reinterpret_cast<const uint2*>(p));
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
+}
+template <> __device__ __forceinline__ float4 img_ld4<__half>(const __half* p) {
+  const uint2 u = __ldcs(reinterpret_cast<const uint2*>(p));
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
 template <typename TT>
 __global__ void __launch_bounds__(256) img_pool_fwd_kernel(const TT* __restrict__ tokens, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float* __restrict__ out,
@@ -15,22 +27,31 @@ __global__ void __launch_bounds__(256) img_pool_fwd_kernel(const TT* __restrict_
   __shared__ float bc[2];
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const TT* tk = tokens + (int64_t)b * n_tok * d;
-  float v[4];   // d <= 1024
+  // thread t owns the 4 adjacent columns 4t .. 4t+3 (d <= 1024, d % 4 == 0): 16-byte (fp32) / 8-byte (16-bit) loads, eight
+  // token rows in flight per thread (the scalar one-row-at-a-time loop ran at 41 % of DRAM peak)
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
   float sum = 0.f;
+  const int c0 = threadIdx.x * 4;
+  if (c0 < d) {
+    if (pool_cls) {
+      const float4 x = img_ld4<TT>(tk + c0);
+      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+    } else {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int t = 0;
+      for (; t + 8 <= n_tok; t += 8) {
+        float4 x[8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int c = threadIdx.x + 256 * i;
-    v[i] = 0.f;
-    if (c < d) {
-      if (pool_cls) v[i] = to_f<TT>(tk[c]);
-      else {
-        float acc = 0.f;
-        for (int t = 0; t < n_tok; ++t) acc += to_f<TT>(tk[(int64_t)t * d + c]);
-        v[i] = acc / (float)n_tok;
+        for (int u = 0; u < 8; ++u) x[u] = img_ld4<TT>(tk + (int64_t)(t + u) * d + c0);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { acc.x += x[u].x; acc.y += x[u].y; acc.z += x[u].z; acc.w += x[u].w; }
       }
-      pooled[(int64_t)b * d + c] = v[i];
-      sum += v[i];
+      for (; t < n_tok; ++t) { const float4 x = img_ld4<TT>(tk + (int64_t)t * d + c0); acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w; }
+      const float inv = 1.f / (float)n_tok;
+      v[0] = acc.x * inv; v[1] = acc.y * inv; v[2] = acc.z * inv; v[3] = acc.w * inv;
     }
+    *reinterpret_cast<float4*>(pooled + (int64_t)b * d + c0) = make_float4(v[0], v[1], v[2], v[3]);
+    sum = v[0] + v[1] + v[2] + v[3];
   }
   sum = warp_sum(sum);
   if (lane == 0) red[warp] = sum;
@@ -39,8 +60,10 @@ __global__ void __launch_bounds__(256) img_pool_fwd_kernel(const TT* __restrict_
   __syncthreads();
   const float mean = bc[0];
   float sq = 0.f;
+  if (c0 < d) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { const int c = threadIdx.x + 256 * i; if (c < d) sq += (v[i] - mean) * (v[i] - mean); }
+    for (int i = 0; i < 4; ++i) sq += (v[i] - mean) * (v[i] - mean);
+  }
   sq = warp_sum(sq);
   if (lane == 0) red[warp] = sq;
   __syncthreads();
@@ -48,10 +71,10 @@ __global__ void __launch_bounds__(256) img_pool_fwd_kernel(const TT* __restrict_
   __syncthreads();
   const float rstd = bc[1];
   if (threadIdx.x == 0) { stats[b * 2] = mean; stats[b * 2 + 1] = rstd; }
+  if (c0 < d) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int c = threadIdx.x + 256 * i;
-    if (c < d) {
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + i;
       float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
       if (thresh != 0) o = drop_keep(k0, k1, (uint64_t)b * d + c, thresh) ? o * scale : 0.f;
       out[(int64_t)b * d + c] = o;
@@ -131,7 +154,8 @@ using namespace mmoe;
 extern "C" int mmoe_img_pool_fwd(const mmoe_call* c, const void* tokens, int tok_dtype, int32_t n_tok, int32_t d, int32_t pool_cls,
                                  float* out, float* stats, float* pooled) {
   if (c->B == 0) return 0;
-  MMOE_CHECK(d <= 1024, "img_pool: d must be <= 1024");
+  MMOE_CHECK(d <= 1024 && d % 4 == 0, "img_pool: d must be a multiple of 4, <= 1024");
+  MMOE_CHECK((reinterpret_cast<uintptr_t>(tokens) & 15) == 0, "img_pool: tokens must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)c->stream;
   const float p = c->training ? c->drop_p : 0.f;
   uint32_t k0, k1;

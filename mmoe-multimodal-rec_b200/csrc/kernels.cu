@@ -92,23 +92,34 @@ __global__ void cast_drop_colsum_kernel(const float* __restrict__ x, const T* __
   const int64_t r1 = min(rows, r0 + rpb);
   for (int c = blockIdx.y * 1024 + threadIdx.x * 4; c < min(cols, (int)(blockIdx.y + 1) * 1024); c += 1024) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t r = r0; r < r1; ++r) {
-      float4 v = x != nullptr ? load4<float>(x + r * cols + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (x_t != nullptr) { const float4 e = load4<T>(x_t + r * cols + c); v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w; }
-      if (thresh != 0) {
-        const uint64_t idx = (uint64_t)r * cols + c;
-        v.x = drop_keep(k0, k1, idx + 0, thresh) ? v.x * scale : 0.f;
-        v.y = drop_keep(k0, k1, idx + 1, thresh) ? v.y * scale : 0.f;
-        v.z = drop_keep(k0, k1, idx + 2, thresh) ? v.z * scale : 0.f;
-        v.w = drop_keep(k0, k1, idx + 3, thresh) ? v.w * scale : 0.f;
+    // four rows per trip: their loads are issued together (the one-row loop ran at 20 % of DRAM peak on [32768, 768])
+    for (int64_t r = r0; r < r1; r += 4) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r + u < r1) {
+          if (x != nullptr) v[u] = load4<float>(x + (r + u) * cols + c);
+          if (x_t != nullptr) { const float4 e = load4<T>(x_t + (r + u) * cols + c); v[u].x += e.x; v[u].y += e.y; v[u].z += e.z; v[u].w += e.w; }
+        }
       }
-      if (g != nullptr) {
-        store4<T>(g + r * cols + c, v);
-        // column sums are taken over the values as stored (rounded to T)
-        const float4 w = load4<T>(g + r * cols + c);
-        v = w;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (r + u >= r1) break;
+        float4 w = v[u];
+        if (thresh != 0) {
+          const uint64_t idx = (uint64_t)(r + u) * cols + c;
+          w.x = drop_keep(k0, k1, idx + 0, thresh) ? w.x * scale : 0.f;
+          w.y = drop_keep(k0, k1, idx + 1, thresh) ? w.y * scale : 0.f;
+          w.z = drop_keep(k0, k1, idx + 2, thresh) ? w.z * scale : 0.f;
+          w.w = drop_keep(k0, k1, idx + 3, thresh) ? w.w * scale : 0.f;
+        }
+        if (g != nullptr) {
+          store4<T>(g + (r + u) * cols + c, w);
+          w = round4<T>(w);               // column sums are taken over the values as stored (rounded to T)
+        }
+        acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
       }
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     if (colsum != nullptr) {
       atomicAdd(colsum + c + 0, acc.x); atomicAdd(colsum + c + 1, acc.y);
