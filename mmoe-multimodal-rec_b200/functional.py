@@ -17,6 +17,12 @@ from ._lib import BF16, F16, F32, Call, CrossCfg, FuseCfg, HeadCfg, HomeCfg, che
 
 # test hook: when set to a list, CrossFn / FuseFn append (kind, cfg, home, B, dtype, saved_blob) after forward
 DEBUG_SAVED = None
+# RobustTextCrossExpert backward as a chain of autograd stages (gradients reach DDP's reducer layer by layer, its all-reduce
+# overlaps the rest of backward) or as one node (MMOE_CROSS_STAGED=0: all of the expert's gradients appear at the end)
+import os as _os
+CROSS_STAGED = _os.environ.get("MMOE_CROSS_STAGED", "1") != "0"
+# native exchange: start each collective when its stage is enqueued (overlap) or all of them at the end of backward
+NATIVE_DEFER = _os.environ.get("MMOE_NATIVE_DEFER", "0") == "1"
 
 _TORCH2MMOE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 _MMOE2TORCH = {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}
@@ -159,11 +165,15 @@ class _GradSync:
         self.avg = dist.get_backend(group) == "nccl"
         self.sync = True             # False = accumulate locally (the equivalent of DDP.no_sync())
         self.pending = []            # (work, tensor to divide afterwards or None)
+        self.late = []               # NATIVE_DEFER: buffers whose collective starts at the end of the backward pass
         self.deferred = []           # (params, views, flat): installed into .grad by finish()
         self.callback_queued = False
 
-    def reduce(self, flat: torch.Tensor):
+    def reduce(self, flat: torch.Tensor, now: bool = False):
         if self.world == 1 or flat.numel() == 0 or not self.sync:
+            return
+        if NATIVE_DEFER and not now and self._ensure_callback():
+            self.late.append(flat)
             return
         if self.avg:
             w = self.dist.all_reduce(flat, op=self.dist.ReduceOp.AVG, group=self.group, async_op=True)
@@ -175,6 +185,10 @@ class _GradSync:
     def defer(self, params, views, flat):
         """Hand the gradients of `params` (views of `flat`) over for installation at the end of the backward pass."""
         self.deferred.append((list(params), list(views), flat))
+        self._ensure_callback()
+
+    def _ensure_callback(self) -> bool:
+        """Queue finish() on the autograd engine (runs when the current backward pass ends); False outside a backward pass."""
         if not self.callback_queued:
             self.callback_queued = True
             try:
@@ -182,6 +196,7 @@ class _GradSync:
             except RuntimeError:
                 # not inside a backward pass (direct call in a test): the caller runs wait_grad_allreduce()
                 self.callback_queued = False
+        return self.callback_queued
 
     def wait(self):
         for w, t in self.pending:
@@ -192,6 +207,9 @@ class _GradSync:
 
     def finish(self):
         self.callback_queued = False
+        for flat in self.late:
+            self.reduce(flat, now=True)
+        self.late.clear()
         self.wait()
         for params, views, flat in self.deferred:
             _install_grads(params, views, flat)

@@ -124,7 +124,7 @@ class RobustTextCrossExpert(_Native):
         used = self._used(pack.names)
 
         def run(u, um, i, im):
-            if torch.is_grad_enabled():
+            if torch.is_grad_enabled() and Fn.CROSS_STAGED:
                 # staged backward: parameter gradients become available layer by layer (DDP overlap)
                 return Fn.cross_expert_staged(pack, cfg, self._home, used, self.training, self._drop_p, u, um, i, im, params)
             return Fn.CrossFn.apply(pack, cfg, self._home, used, self.training, self._drop_p, u, um, i, im, *params)

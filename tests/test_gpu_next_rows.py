@@ -279,3 +279,80 @@ def test_sentence_gather_train_mode_and_16bit_hidden_states():
     assert nerr(sent, so) <= 1e-5 and nerr(doc, do) <= 1e-5
     assert nerr(hc.grad.float(), ho.grad) <= 1e-2                      # gradient handed back in bf16, the dtype of h
     assert nerr(norm.weight.grad, wo.grad) <= 1e-4 and nerr(norm.bias.grad, bo.grad) <= 1e-4
+
+
+# ------------------------------------------------------------------------------------------ out-of-bounds writes
+def test_new_kernels_do_not_write_outside_their_outputs():
+    """compute-sanitizer is closed on this pool, so the new kernels are called through the C ABI with every output embedded
+    in a larger buffer of sentinels (ragged sizes on purpose); the bands around the outputs must come back untouched."""
+    import mmoe_multimodal_rec_b200 as pkg
+    from mmoe_multimodal_rec_b200 import _lib as LB
+    L = pkg.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    PAD = 4096
+
+    class Guard:
+        def __init__(self, numel, dtype):
+            self.buf = torch.full((numel + 2 * PAD,), 77, dtype=dtype, device="cuda")
+            self.view = self.buf[PAD:PAD + numel]
+            self.n = numel
+
+        def ok(self):
+            return bool((self.buf[:PAD] == 77).all()) and bool((self.buf[PAD + self.n:] == 77).all())
+
+    def ptrs(ts):
+        return LB.ptr_array([t.data_ptr() for t in ts])
+    # 6-way BN-SiLU-dropout-stack, B = 37
+    B, n, d = 37, 6, 768
+    xs = [torch.randn(B, d, device="cuda") for _ in range(n)]
+    prm = [torch.ones(d, device="cuda") if i % 2 == 0 else torch.zeros(d, device="cuda") for i in range(2 * n)]
+    rm, rv = [torch.zeros(d, device="cuda") for _ in range(n)], [torch.ones(d, device="cuda") for _ in range(n)]
+    out, sm, sr = Guard(B * n * d, torch.float32), Guard(n * d, torch.float32), Guard(n * d, torch.float32)
+    c = LB.Call(); c.dtype, c.B, c.training, c.drop_p, c.seed, c.stream = 0, B, 1, 0.1, 5, st
+    pa = ptrs(prm); c.params = Ct.cast(pa, Ct.POINTER(Ct.c_void_p))
+    assert L.mmoe_bn_silu_stack_fwd(Ct.byref(c), n, d, ptrs(xs), out.view.data_ptr(), sm.view.data_ptr(), sr.view.data_ptr(), ptrs(rm), ptrs(rv), 0.1, 1e-5) == 0
+    dxs = [Guard(B * d, torch.float32) for _ in range(n)]
+    grads = [Guard(d, torch.float32) for _ in range(2 * n)]
+    ga = ptrs([g.view for g in grads]); c.grads = Ct.cast(ga, Ct.POINTER(Ct.c_void_p))
+    dout = torch.randn(B, n, d, device="cuda")
+    assert L.mmoe_bn_silu_stack_bwd(Ct.byref(c), n, d, ptrs(xs), dout.data_ptr(), sm.view.data_ptr(), sr.view.data_ptr(), ptrs(rm), ptrs(rv),
+                                    ptrs([g.view for g in dxs]), 1e-5) == 0
+    torch.cuda.synchronize()
+    assert out.ok() and sm.ok() and sr.ok() and all(g.ok() for g in dxs) and all(g.ok() for g in grads)
+    # sentence gather, B = 5, S = 7 (not a multiple of the 8 warps), d = 768
+    Bs, S = 5, 7
+    h = torch.randn(11 * 13, d, device="cuda")
+    src = torch.randint(-1, 11 * 13, (Bs, S), dtype=torch.int32, device="cuda")
+    sent, mask, doc = Guard(Bs * S * d, torch.float32), Guard(Bs * S, torch.uint8), Guard(Bs * d, torch.float32)
+    pre, stats = Guard(Bs * d, torch.float32), Guard(Bs * (S + 1) * 2, torch.float32)
+    c2 = LB.Call(); c2.dtype, c2.B, c2.training, c2.drop_p, c2.seed, c2.stream = 0, Bs, 1, 0.1, 9, st
+    nw = [torch.ones(d, device="cuda"), torch.zeros(d, device="cuda")]
+    pa2 = ptrs(nw); c2.params = Ct.cast(pa2, Ct.POINTER(Ct.c_void_p))
+    assert L.mmoe_sent_gather_fwd(Ct.byref(c2), S, d, h.data_ptr(), 0, src.data_ptr(), sent.view.data_ptr(), mask.view.data_ptr(), doc.view.data_ptr(),
+                                  pre.view.data_ptr(), stats.view.data_ptr()) == 0
+    dh, dgw = Guard(h.numel(), torch.float32), [Guard(d, torch.float32), Guard(d, torch.float32)]
+    dh.view.zero_(); [g.view.zero_() for g in dgw]
+    ga2 = ptrs([g.view for g in dgw]); c2.grads = Ct.cast(ga2, Ct.POINTER(Ct.c_void_p))
+    ds, dd = torch.randn(Bs, S, d, device="cuda"), torch.randn(Bs, d, device="cuda")
+    assert L.mmoe_sent_gather_bwd(Ct.byref(c2), S, d, h.data_ptr(), 0, src.data_ptr(), mask.view.data_ptr(), pre.view.data_ptr(), stats.view.data_ptr(),
+                                  ds.data_ptr(), dd.data_ptr(), dh.view.data_ptr()) == 0
+    torch.cuda.synchronize()
+    assert sent.ok() and mask.ok() and doc.ok() and pre.ok() and stats.ok() and dh.ok() and all(g.ok() for g in dgw)
+    # patch bytes -> operand, float image -> operand (3 images), bf16
+    raw = torch.randint(0, 256, (3 * 196, 768), dtype=torch.uint8, device="cuda")
+    op1, op2 = Guard(3 * 196 * 768, torch.bfloat16), Guard(3 * 196 * 768, torch.bfloat16)
+    assert L.mmoe_patch_u8_to_operand(raw.data_ptr(), op1.view.data_ptr(), 3 * 196, 768, 1, st) == 0
+    img = torch.randn(3, 3, 224, 224, device="cuda")
+    assert L.mmoe_patchify(img.data_ptr(), op2.view.data_ptr(), 3, 3, 224, 224, 16, 1, st) == 0
+    # AUC workspace, n = 4099
+    nb = L.mmoe_auc_workspace_bytes(4099)
+    work, res = Guard(nb // 8, torch.int64), Guard(1, torch.float64)
+    sc, lb = torch.randn(4099, device="cuda"), (torch.rand(4099, device="cuda") < 0.5).float()
+    assert L.mmoe_auc(sc.data_ptr(), lb.data_ptr(), 4099, work.view.data_ptr(), nb, res.view.data_ptr(), st) == 0
+    # BCE
+    lg = Guard(2 * 37, torch.float32); lossb = Guard(1, torch.float32); lossb.view.zero_()
+    x = torch.randn(2 * 37, device="cuda"); yy = (torch.rand(37, device="cuda") < 0.5).float()
+    assert L.mmoe_bce2_fwd_bwd(x.data_ptr(), yy.data_ptr(), yy.data_ptr(), 1.0, 2.0, 37, lossb.view.data_ptr(), lg.view.data_ptr(), 1.0, st) == 0
+    torch.cuda.synchronize()
+    assert op1.ok() and op2.ok() and work.ok() and res.ok() and lg.ok() and lossb.ok()
+    assert torch.equal(op1.view.view(3 * 196, 768).float(), raw.float())
