@@ -164,12 +164,19 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # the reference's composition on stock torch modules (oracle/eager_ref.py): CPU arm and eager-on-B200 arm
 # ----------------------------------------------------------------------------------------------
-def build_modules(dev, train=True, seed=1234):
+def build_modules(dev, train=True, seed=1234, fused=None):
+    """fused: None = the package default (MMOE_FLAT_PARAMS), True/False = fused-parameter / per-tensor modules."""
     import mmoe_multimodal_rec_b200 as pkg
     M = pkg.modules
     torch.manual_seed(seed)
-    mods = {"img": M.ItemImageExpert(Passthrough(), pool_type="mean"), "cross": M.RobustTextCrossExpert(),
-            "concat_ui": M.EnhancedCrossFuse(), "concat_ti": M.EnhancedCrossFuse(), "head": M.TwoTaskMMoE()}
+    was = pkg.functional.FLAT_PARAMS
+    if fused is not None:
+        pkg.functional.set_flat_parameters(fused)
+    try:
+        mods = {"img": M.ItemImageExpert(Passthrough(), pool_type="mean"), "cross": M.RobustTextCrossExpert(),
+                "concat_ui": M.EnhancedCrossFuse(), "concat_ti": M.EnhancedCrossFuse(), "head": M.TwoTaskMMoE()}
+    finally:
+        pkg.functional.set_flat_parameters(was)
     for m in mods.values():
         m.to(dev).train(train)
     return mods
@@ -453,6 +460,9 @@ def main():
     ap.add_argument("--exchange", default="both", choices=["ddp", "native", "both"],
                     help="N > 1: which gradient exchange to time; the headline is always the DDP wrappers when measured")
     ap.add_argument("--ddp-view", action="store_true", help="gradient_as_bucket_view=True on the DDP wrappers (train.py passes nothing)")
+    ap.add_argument("--params", default="default", choices=["default", "tensor", "fused"],
+                    help="parameter layout of the modules: per-tensor nn.Parameters, one fused nn.Parameter per module "
+                         "(MMOE_FLAT_PARAMS=1), or the package default")
     ap.add_argument("--nccl-ctas", type=int, default=0,
                     help="N>1: if > 0, cap NCCL at this many CTAs and keep as many SMs free of GEMM CTAs")
     args = ap.parse_args()
@@ -490,14 +500,22 @@ def main():
     if distributed and args.nccl_ctas > 0:
         L.mmoe_set_sm_reserve(args.nccl_ctas)
 
-    mods_d = build_modules(dev, train=not args.eval_mode)
-    img, cross, cui, cti, head = (mods_d[k] for k in ("img", "cross", "concat_ui", "concat_ti", "head"))
-    mods = [img, cross, cui, cti, head]
-    if distributed:
-        for m in mods:
-            for prm in m.parameters():
-                dist.broadcast(prm.data, src=0)
-    call = {"cross": cross, "cui": cui, "cti": cti, "head": head}
+    fused = {"default": pkg.functional.FLAT_PARAMS, "tensor": False, "fused": True}[args.params]
+
+    def make_modules(fused_mode):
+        md = build_modules(dev, train=not args.eval_mode, fused=fused_mode)
+        ms = [md[k] for k in ("img", "cross", "concat_ui", "concat_ti", "head")]
+        if distributed:
+            for m in ms:
+                for prm in m.parameters():
+                    dist.broadcast(prm.data, src=0)
+        return ms
+
+    mods = make_modules(fused)
+    img, cross, cui, cti, head = mods
+    call = {"img": img, "cross": cross, "cui": cui, "cti": cti, "head": head}
+    params_note = ("one fused nn.Parameter per module (MMOE_FLAT_PARAMS=1 / functional.set_flat_parameters; state_dict keys unchanged)"
+                   if fused else "one nn.Parameter per tensor, as in the reference")
     pw_g = torch.tensor(POS_W_GOOD, device=dev)
     pw_b = torch.tensor(POS_W_BEST, device=dev)
 
@@ -515,13 +533,21 @@ def main():
 
     all_params = [p for m in mods for p in m.parameters()]
 
+    def ddp_wrap(ms):
+        # the reference scripts' way (train.py:136-139): one DistributedDataParallel wrapper per module, default arguments;
+        # the head is called through .module (train.py:251), so its gradient is not exchanged
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        kw = {"gradient_as_bucket_view": True} if args.ddp_view else {}
+        w = {k: DDP(m, device_ids=[local_rank], **kw) for k, m in zip(("cross", "cui", "cti", "head"), ms[1:])}
+        return {"img": ms[0], "cross": w["cross"], "cui": w["cui"], "cti": w["cti"], "head": w["head"].module}
+
     def step(b):
         for p in all_params:                 # what optimizer.zero_grad() does (train.py:288): walk a flat parameter list
             p.grad = None
         ins = {k: (v.detach().requires_grad_(True) if k in grad_keys else v) for k, v in b.items()}
         cross_c, cui_c, cti_c, head_c = call["cross"], call["cui"], call["cti"], call["head"]
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            img_vec = img(ins["img_tokens"], trainable=False)
+            img_vec = call["img"](ins["img_tokens"], trainable=False)
             side = side_stream if use_side[0] else None
             if side is not None:
                 # the two fuse experts are independent, latency-bound chains of ~100 small launches each (2 tokens per
@@ -611,14 +637,32 @@ def main():
                                 "into .grad by an engine callback at the end of backward; no per-parameter hooks or bucket copies"}
         pkg.functional.disable_grad_allreduce()
     exchange = "none"
+    other_ddp = None
+    if distributed and args.exchange == "both":
+        # the DDP wrappers around modules with the OTHER parameter layout, timed next to the headline
+        o_mods = make_modules(not fused)
+        keep = (dict(call), list(all_params))
+        call.update(ddp_wrap(o_mods))
+        all_params[:] = [p for m in o_mods for p in m.parameters()]
+        for _ in range(W):
+            step(resident)
+        barrier()
+        timed_loop(args.steps)
+        ms_o, _, _, _, _ = timed_loop(args.steps)
+        ms_o = max_over_ranks(ms_o) / args.steps
+        other_ddp = {"parameters": "one nn.Parameter per tensor, as in the reference" if fused else
+                                   "one fused nn.Parameter per module (MMOE_FLAT_PARAMS=1)",
+                     "value": B * world / (ms_o * 1e-3), "unit": UNIT, "ms_per_step": ms_o,
+                     "how": "the same DistributedDataParallel wrappers (default arguments) around modules with the other parameter layout"}
+        call.update(keep[0])
+        all_params[:] = keep[1]
+        del o_mods
+        gc.collect()
+        torch.cuda.empty_cache()
     if distributed and args.exchange in ("ddp", "both"):
-        # the reference scripts' way (train.py:136-139): one DistributedDataParallel wrapper per module, default arguments;
-        # the head is called through .module (train.py:251), so its gradient is not exchanged
-        from torch.nn.parallel import DistributedDataParallel as DDP
-        kw = {"gradient_as_bucket_view": True} if args.ddp_view else {}
-        wrapped = {k: DDP(m, device_ids=[local_rank], **kw) for k, m in (("cross", cross), ("cui", cui), ("cti", cti), ("head", head))}
-        call = {"cross": wrapped["cross"], "cui": wrapped["cui"], "cti": wrapped["cti"], "head": wrapped["head"].module}
-        exchange = "torch DistributedDataParallel, one wrapper per module, default arguments (train.py:136-139); head via .module (train.py:251)"
+        call.update(ddp_wrap(mods))
+        exchange = ("torch DistributedDataParallel, one wrapper per module, default arguments (train.py:136-139); head via .module "
+                    "(train.py:251); module parameters: " + params_note)
     elif distributed:
         pkg.functional.enable_grad_allreduce()
         exchange = "native flat-buffer all-reduce (functional.enable_grad_allreduce)"
@@ -806,6 +850,9 @@ def main():
         }
         if native_result is not None:
             line["native_exchange"] = native_result
+        if other_ddp is not None:
+            line["ddp_other_parameter_layout"] = other_ddp
+        line["config"]["parameters"] = params_note
         if home_ddp is not None:
             line["extra"] = {"home_step_ddp_fwd_bwd_bf16": home_ddp}
         if world == 1 and not args.no_extras:

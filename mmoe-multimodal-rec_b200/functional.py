@@ -23,6 +23,16 @@ import os as _os
 CROSS_STAGED = _os.environ.get("MMOE_CROSS_STAGED", "1") != "0"
 # native exchange: start each collective when its stage is enqueued (overlap) or all of them at the end of backward
 NATIVE_DEFER = _os.environ.get("MMOE_NATIVE_DEFER", "0") == "1"
+# fused-parameter mode (the default; MMOE_FLAT_PARAMS=0 or set_flat_parameters(False) before construction turns it off):
+# modules built while this is on keep all of their (used) parameters in ONE nn.Parameter whose storage the reference-named
+# attributes view (modules._Native.fuse_parameters); state_dict keys, order and shapes are unchanged
+FLAT_PARAMS = _os.environ.get("MMOE_FLAT_PARAMS", "1") != "0"
+
+
+def set_flat_parameters(on: bool):
+    """Modules constructed after this call are (on=True) / are not (on=False) in fused-parameter mode."""
+    global FLAT_PARAMS
+    FLAT_PARAMS = bool(on)
 
 _TORCH2MMOE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 _MMOE2TORCH = {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}
@@ -121,10 +131,11 @@ def _grad_layout(params: Sequence[torch.Tensor], used: Sequence[bool]):
     return lay
 
 
-def _alloc_grads(params: Sequence[torch.Tensor], used: Sequence[bool]):
+def _alloc_grads(params: Sequence[torch.Tensor], used: Sequence[bool], want_views: bool = True):
     """One zeroed fp32 buffer holding the gradients of all used parameters (each at a 256-byte aligned offset); returns
     (views, pointer list, flat buffer).  One as_strided per parameter: the view creation is host time on the critical
-    path of every backward (≈300 parameters per step)."""
+    path of every backward (≈300 parameters per step).  want_views=False (fused-parameter modules, whose single
+    parameter takes the flat buffer itself as its gradient): views is None."""
     total, entries = _grad_layout(params, used)
     flat = torch.zeros(total, dtype=torch.float32, device=params[0].device)
     base = flat.data_ptr()
@@ -134,9 +145,10 @@ def _alloc_grads(params: Sequence[torch.Tensor], used: Sequence[bool]):
             views.append(None)
             ptrs.append(None)
         else:
-            views.append(flat.as_strided(e[1], e[2], e[0]))
+            if want_views:
+                views.append(flat.as_strided(e[1], e[2], e[0]))
             ptrs.append(base + 4 * e[0])
-    return views, ptrs, flat
+    return (views if want_views else None), ptrs, flat
 
 
 # ----------------------------------------------------------------------------------------------
@@ -319,6 +331,33 @@ def _hand_over(params, views, req, flat):
     return [None] * len(out)
 
 
+def _split_fused(pack: "ParamPack", params):
+    """Modules in fused-parameter mode (modules._Native.fuse_parameters) pass their parameter VIEWS (plain tensors, no
+    autograd) followed by the one nn.Parameter that owns the storage; returns (per-name tensors, that parameter or None)."""
+    if getattr(pack, "fused", False):
+        return params[:-1], params[-1]
+    return params, None
+
+
+def _param_grads(ctx, pt, used):
+    """(views, grad pointer list, flat) for a backward whose forward stored ctx.flat_p."""
+    return _alloc_grads(pt, used, want_views=ctx.flat_p is None)
+
+
+def _finish_params(ctx, views, flat):
+    """The trailing entries of a backward's return value: one gradient per parameter input of the forward."""
+    if ctx.flat_p is None:
+        return _hand_over(ctx.params, views, ctx.param_req, flat)
+    # fused mode: the flat buffer IS the gradient of the module's single parameter (same layout by construction)
+    fp = ctx.flat_p
+    if tuple(flat.shape) != tuple(fp.shape):
+        raise RuntimeError("mmoe_b200: fused parameter layout changed after fuse_parameters() (got %s, expected %s)"
+                           % (tuple(fp.shape), tuple(flat.shape)))
+    g = _hand_over([fp], [flat], [fp.requires_grad], flat)
+    ctx.flat_p = None
+    return [None] * len(ctx.param_req) + list(g)
+
+
 def _span(flat: torch.Tensor, views, lo: int, hi: int):
     """The contiguous slice of `flat` that holds views[lo:hi] (None entries skipped)."""
     vs = [v for v in views[lo:hi] if v is not None]
@@ -373,6 +412,7 @@ class HeadFn(torch.autograd.Function):
         dtype = compute_dtype()
         ev = _f32c(expert_vecs)
         B, dev = ev.shape[0], ev.device
+        params, ctx.flat_p = _split_fused(pack, params)
         pt = pack.tensors(params, dtype)
         fwd, bwd, sb, wb = ((L.mmoe_head_fwd, L.mmoe_head_bwd, L.mmoe_head_saved_bytes, L.mmoe_head_workspace_bytes) if kind == "mmoe"
                             else (L.mmoe_home_fwd, L.mmoe_home_bwd, L.mmoe_home_saved_bytes, L.mmoe_home_workspace_bytes))
@@ -399,14 +439,14 @@ class HeadFn(torch.autograd.Function):
         pack, kind, cfg, training, drop_p, seed, dtype, ev, pt, saved, bwd, wb = _state(ctx)
         L = lib()
         B, dev = ev.shape[0], ev.device
-        views, gptrs, flat = _alloc_grads(pt, [True] * ctx.n_params)
+        views, gptrs, flat = _param_grads(ctx, pt, [True] * ctx.n_params)
         work = _bytes(wb(C.byref(cfg), B, dtype), dev)
         d_ev = torch.empty_like(ev)
         dl = _f32c(dlogits)
         c = _call(dtype, B, training, 0, drop_p, seed, pt, gptrs, saved, work)
         check(bwd(C.byref(c), C.byref(cfg), ev.data_ptr(), dl.data_ptr(), d_ev.data_ptr()), kind + "_bwd")
         _sync_grads(flat)
-        grads = _hand_over(ctx.params, views, ctx.param_req, flat)
+        grads = _finish_params(ctx, views, flat)
         ctx.state = ctx.params = None           # release the saved blob / inputs / 16-bit weights with the pass
         return (None, None, None, None, None, None, d_ev.to(ctx.in_dtype), *grads)
 
@@ -428,6 +468,7 @@ class CrossFn(torch.autograd.Function):
         um = user_mask.detach().to(torch.bool).contiguous().view(torch.uint8)
         im = item_mask.detach().to(torch.bool).contiguous().view(torch.uint8)
         B, dev = u.shape[0], u.device
+        params, ctx.flat_p = _split_fused(pack, params)
         pt = pack.tensors(params, dtype)
         saved = _bytes(L.mmoe_cross_saved_bytes(C.byref(cfg), B, dtype), dev)
         out = torch.empty((B, cfg.d), dtype=torch.float32, device=dev)
@@ -448,7 +489,7 @@ class CrossFn(torch.autograd.Function):
         cfg, home, used, training, drop_p, seed, dtype, u, um, it, im, pt, saved = _state(ctx)
         L = lib()
         B, dev = u.shape[0], u.device
-        views, gptrs, flat = _alloc_grads(pt, used)
+        views, gptrs, flat = _param_grads(ctx, pt, used)
         work = _bytes(L.mmoe_cross_workspace_bytes(C.byref(cfg), B, dtype), dev)
         d_user, d_item = torch.empty_like(u), torch.empty_like(it)
         do = _f32c(dout)
@@ -456,7 +497,7 @@ class CrossFn(torch.autograd.Function):
         check(L.mmoe_cross_bwd(C.byref(c), C.byref(cfg), u.data_ptr(), um.data_ptr(), it.data_ptr(), im.data_ptr(), do.data_ptr(),
                                d_user.data_ptr(), d_item.data_ptr()), "cross_bwd")
         _sync_grads(flat)
-        grads = _hand_over(ctx.params, views, ctx.param_req, flat)
+        grads = _finish_params(ctx, views, flat)
         ctx.state = ctx.params = None
         return (None, None, None, None, None, None, d_user.to(ctx.in_dtypes[0]), None, d_item.to(ctx.in_dtypes[1]), None, *grads)
 
@@ -633,6 +674,7 @@ class FuseFn(torch.autograd.Function):
         dtype = compute_dtype()
         v, t = _f32c(v_cls), _f32c(t_cls)
         B, dev = v.shape[0], v.device
+        params, ctx.flat_p = _split_fused(pack, params)
         pt = pack.tensors(params, dtype)
         saved = _bytes(L.mmoe_fuse_saved_bytes(C.byref(cfg), B, dtype), dev)
         out = torch.empty((B, cfg.d), dtype=torch.float32, device=dev)
@@ -652,14 +694,14 @@ class FuseFn(torch.autograd.Function):
     def backward(ctx, dout):
         cfg, home, used, training, drop_p, seed, dtype, B, dev, pt, saved = _state(ctx)
         L = lib()
-        views, gptrs, flat = _alloc_grads(pt, used)
+        views, gptrs, flat = _param_grads(ctx, pt, used)
         work = _bytes(L.mmoe_fuse_workspace_bytes(C.byref(cfg), B, dtype), dev)
         d_cat = torch.empty((B, 2, cfg.d), dtype=torch.float32, device=dev)
         do = _f32c(dout)
         c = _call(dtype, B, training, home, drop_p, seed, pt, gptrs, saved, work)
         check(L.mmoe_fuse_bwd(C.byref(c), C.byref(cfg), do.data_ptr(), d_cat.data_ptr()), "fuse_bwd")
         _sync_grads(flat)
-        grads = _hand_over(ctx.params, views, ctx.param_req, flat)
+        grads = _finish_params(ctx, views, flat)
         ctx.state = ctx.params = None
         return (None, None, None, None, None, None, d_cat[:, 0].to(ctx.in_dtypes[0]), d_cat[:, 1].to(ctx.in_dtypes[1]), *grads)
 

@@ -39,24 +39,77 @@ def _standalone(module, owner: str):
         f"B200-native package has no stand-alone (torch eager) forward for it.  Call the owning module.")
 
 
-class _Native(nn.Module):
-    """Shared plumbing: parameter pack in state_dict order + chunked no-grad execution."""
+class _NativeMeta(type):
+    """Runs the fused-parameter step after the most-derived __init__ has returned (the reference scripts construct the
+    modules and hand them straight to .to(device) / DistributedDataParallel, so there is no later hook to do it in)."""
+
+    def __call__(cls, *args, **kwargs):
+        obj = super().__call__(*args, **kwargs)
+        if cls._fusable and Fn.FLAT_PARAMS:
+            obj.fuse_parameters()
+        return obj
+
+
+_FLAT = "_flat_param"
+
+
+class _Native(nn.Module, metaclass=_NativeMeta):
+    """Shared plumbing: parameter pack in state_dict order + chunked no-grad execution + fused-parameter mode.
+
+    Fused-parameter mode (``fuse_parameters()``; automatic for modules built under ``MMOE_FLAT_PARAMS=1`` /
+    ``functional.set_flat_parameters(True)``): every parameter the forward uses moves into ONE ``nn.Parameter``
+    (``_flat_param``, laid out exactly like the flat gradient buffer the backward kernels write), and the reference-named
+    attributes (``mlp[0].weight`` ...) become plain tensor views of it.  ``parameters()`` then yields one tensor per
+    module — which is what the reference scripts hand to AdamW / clip_grad_norm_ / DistributedDataParallel
+    (train.py:159-167, 136-139) — so DDP copies one gradient per module in and out of its buckets instead of ~60, the
+    optimizer updates one tensor, and ``.grad`` is the buffer the kernels wrote, never re-packed.  ``state_dict()`` /
+    ``load_state_dict()`` keep the reference's keys, order and shapes (hooks below), so checkpoints are interchangeable
+    with the unfused modules and the reference.  What changes for callers: ``named_parameters()`` shows ``_flat_param``
+    instead of the per-tensor names (per-name parameter groups need the unfused mode), per-tensor ``.grad`` attributes do
+    not exist (slice ``_flat_param.grad`` with ``fused_layout()``), and the 64-float padding between tensors is part of
+    the parameter (always zero, zero gradient).  Parameters the HoME variants never use stay ordinary nn.Parameters
+    whose ``.grad`` stays None, as in the reference."""
 
     _lowp_exclude = ()
+    _fusable = False
+
+    def _used(self, names):
+        return [True] * len(names)
 
     def _pack(self):
         pk = self.__dict__.get("_mmoe_pack")
         if pk is None:
-            names, params = _named(self)
+            names, params = self._names_and_tensors()
             lowp = [n for n, p in zip(names, params) if _is_gemm_weight(n, p, self._lowp_exclude)]
             pk = Fn.ParamPack(names, lowp)
+            pk.fused = "_mmoe_fused" in self.__dict__
             self.__dict__["_mmoe_pack"] = pk
         return pk
+
+    def _names_and_tensors(self):
+        """(names in state_dict order, the tensor behind each name: nn.Parameter, or view of the fused parameter)."""
+        specs = self.__dict__.get("_mmoe_fused")
+        if specs is None:
+            return _named(self)
+        flat = self._parameters[_FLAT]
+        if flat.data_ptr() != self.__dict__.get("_mmoe_flat_ptr") or flat.device != self.__dict__.get("_mmoe_flat_dev"):
+            self._rebuild_views()            # .to() / .data swap / deepcopy moved the storage
+        rest = dict(self.named_parameters())
+        fused = {n: owner.__dict__[leaf] for n, owner, leaf, _ in specs}
+        names = self.__dict__["_mmoe_names"]
+        return names, [fused[n] if n in fused else rest[n] for n in names]
 
     def _params(self):
         # cached: walking named_parameters() of a 60-tensor module costs ~0.1 ms per call, twice per step and module.
         # Parameter objects keep their identity through .to() / load_state_dict(); _apply drops the cache anyway.
+        # Fused mode: the per-name views followed by the fused parameter itself (functional._split_fused).
         ps = self.__dict__.get("_mmoe_params")
+        if "_mmoe_fused" in self.__dict__:
+            flat = self._parameters[_FLAT]
+            if ps is None or flat.data_ptr() != self.__dict__.get("_mmoe_flat_ptr") or ps[-1] is not flat:
+                ps = self._names_and_tensors()[1] + [flat]
+                self.__dict__["_mmoe_params"] = ps
+            return ps
         if ps is None:
             ps = [p for _, p in self.named_parameters()]
             self.__dict__["_mmoe_params"] = ps
@@ -65,7 +118,131 @@ class _Native(nn.Module):
     def _apply(self, fn, *args, **kwargs):
         self.__dict__.pop("_mmoe_params", None)
         self.__dict__.pop("_mmoe_pack", None)
-        return super()._apply(fn, *args, **kwargs)
+        out = super()._apply(fn, *args, **kwargs)
+        if "_mmoe_fused" in self.__dict__:
+            self._rebuild_views()
+        return out
+
+    # ------------------------------------------------------------------ fused-parameter mode
+    def fuse_parameters(self):
+        """Move every used parameter into one nn.Parameter (see the class docstring).  Idempotent; returns self."""
+        if "_mmoe_fused" in self.__dict__:
+            return self
+        names, params = _named(self)
+        used = self._used(names)
+        live = [p for p, u in zip(params, used) if u]
+        if not live:
+            return self
+        if any(p.dtype != torch.float32 for p in live) or len({p.device for p in live}) != 1:
+            raise RuntimeError("fuse_parameters: parameters must be float32 and on one device")
+        if len({p.requires_grad for p in live}) != 1:
+            raise RuntimeError("fuse_parameters: parameters must be all trainable or all frozen")
+        if len({id(p) for p in live}) != len(live):
+            raise RuntimeError("fuse_parameters: tied parameters are not supported")
+        sd_order = list(self.state_dict().keys())
+        total, entries = Fn._grad_layout(params, used)
+        flat = torch.zeros(total, dtype=torch.float32, device=live[0].device)
+        specs = []
+        with torch.no_grad():
+            for n, p, e in zip(names, params, entries):
+                if e is None:
+                    continue
+                flat.as_strided(e[1], e[2], e[0]).copy_(p)
+                owner, _, leaf = n.rpartition(".")
+                specs.append((n, self.get_submodule(owner) if owner else self, leaf, e))
+        for _, owner, leaf, _ in specs:
+            del owner._parameters[leaf]
+        self.register_parameter(_FLAT, nn.Parameter(flat, requires_grad=live[0].requires_grad))
+        self.__dict__["_mmoe_fused"] = specs
+        self.__dict__["_mmoe_names"] = names
+        self.__dict__["_mmoe_sd_order"] = sd_order
+        self._rebuild_views()
+        self._register_state_dict_hook(_fused_state_dict_hook)
+        self.register_load_state_dict_pre_hook(_fused_load_pre_hook)
+        return self
+
+    def _rebuild_views(self):
+        flat = self._parameters[_FLAT]
+        base = flat.detach()                     # shares storage AND version counter: an optimizer step on the fused
+        for _, owner, leaf, e in self.__dict__["_mmoe_fused"]:      # parameter invalidates the 16-bit weight cache
+            owner.__dict__[leaf] = base.as_strided(e[1], e[2], e[0])
+        self.__dict__["_mmoe_flat_ptr"] = flat.data_ptr()
+        self.__dict__["_mmoe_flat_dev"] = flat.device
+        self.__dict__.pop("_mmoe_params", None)
+        self.__dict__.pop("_mmoe_pack", None)
+
+    def fused_layout(self):
+        """{name: (offset, shape)} of the reference-named tensors inside ``_flat_param`` (and its ``.grad``); None when unfused."""
+        specs = self.__dict__.get("_mmoe_fused")
+        if specs is None:
+            return None
+        return {n: (e[0], e[1]) for n, _, _, e in specs}
+
+    def named_gradients(self):
+        """(reference name, gradient or None) for every parameter, fused or not — the per-name view of ``.grad``."""
+        specs = self.__dict__.get("_mmoe_fused")
+        if specs is None:
+            return [(n, p.grad) for n, p in self.named_parameters()]
+        g = self._parameters[_FLAT].grad
+        fused = {n: e for n, _, _, e in specs}
+        rest = dict(self.named_parameters())
+        return [(n, (None if g is None else g.as_strided(fused[n][1], fused[n][2], fused[n][0])) if n in fused else rest[n].grad)
+                for n in self.__dict__["_mmoe_names"]]
+
+    def __deepcopy__(self, memo):
+        # the default deep copy keeps the aliasing of tensors that share a storage, but the per-name views live in the
+        # sub-modules' __dict__ next to cached pointers: rebuild them on the copy rather than rely on that
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        skip = ("_mmoe_params", "_mmoe_pack", "_mmoe_flat_ptr", "_mmoe_flat_dev")
+        for k, v in self.__dict__.items():
+            if k not in skip:
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        if "_mmoe_fused" in new.__dict__:
+            new._rebuild_views()
+        return new
+
+
+def _fused_state_dict_hook(module, state_dict, prefix, local_metadata):
+    specs = module.__dict__.get("_mmoe_fused")
+    if specs is None:
+        return
+    state_dict.pop(prefix + _FLAT, None)
+    if module._parameters[_FLAT].data_ptr() != module.__dict__.get("_mmoe_flat_ptr"):
+        module._rebuild_views()
+    for n, owner, leaf, _ in specs:
+        state_dict[prefix + n] = owner.__dict__[leaf]
+    for k in module.__dict__["_mmoe_sd_order"]:          # the reference's key order
+        if prefix + k in state_dict:
+            state_dict.move_to_end(prefix + k)
+
+
+def _fused_load_pre_hook(module, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+    specs = module.__dict__.get("_mmoe_fused")
+    if specs is None:
+        return
+    flat = module._parameters[_FLAT]
+    if flat.data_ptr() != module.__dict__.get("_mmoe_flat_ptr"):
+        module._rebuild_views()
+    own = state_dict.pop(prefix + _FLAT, None)           # a raw fused tensor is accepted only with the exact layout
+    with torch.no_grad():
+        if own is not None and tuple(own.shape) == tuple(flat.shape):
+            flat.copy_(own)
+        for n, owner, leaf, e in specs:
+            key = prefix + n
+            if key not in state_dict:
+                if own is None:
+                    missing_keys.append(key)
+                continue
+            src = state_dict.pop(key)
+            if tuple(src.shape) != tuple(e[1]):
+                error_msgs.append(f"size mismatch for {key}: copying a param with shape {tuple(src.shape)} from checkpoint, "
+                                  f"the shape in current model is {tuple(e[1])}.")
+                continue
+            owner.__dict__[leaf].copy_(src)
+    state_dict[prefix + _FLAT] = flat.detach()           # satisfies the strict-key check of the module's own loader
 
 
 # ----------------------------------------------------------------------------------------------
@@ -93,6 +270,7 @@ class RobustTextCrossExpert(_Native):
 
     _home = False
     _lowp_exclude = ()
+    _fusable = True
 
     def __init__(self, d=768, n_layer=2, n_head=8, dropout=0.1):
         super().__init__()
@@ -124,7 +302,7 @@ class RobustTextCrossExpert(_Native):
         used = self._used(pack.names)
 
         def run(u, um, i, im):
-            if torch.is_grad_enabled() and Fn.CROSS_STAGED:
+            if torch.is_grad_enabled() and Fn.CROSS_STAGED and not pack.fused:
                 # staged backward: parameter gradients become available layer by layer (DDP overlap)
                 return Fn.cross_expert_staged(pack, cfg, self._home, used, self.training, self._drop_p, u, um, i, im, params)
             return Fn.CrossFn.apply(pack, cfg, self._home, used, self.training, self._drop_p, u, um, i, im, *params)
@@ -141,6 +319,7 @@ class EnhancedCrossFuse(_Native):
 
     _home = False
     _lowp_exclude = ("gate.2.weight",)       # the 384->1 gate row is consumed by a GEMV kernel in fp32
+    _fusable = True
 
     def __init__(self, d=768, n_head=8, depth=2, dropout=0.1):
         super().__init__()
@@ -194,6 +373,7 @@ class TwoTaskMMoE(_Native):
     """Two-task dense-gate MMoE head (reference model.py:527-577)."""
 
     _lowp_exclude = ("fc.weight", "7.weight")   # gate rows and the 128->1 row stay fp32 (GEMV kernels)
+    _fusable = True
 
     def __init__(self, expert_dim: int = 768, n_expert: int = 6, tower_hidden: int = 256, tower_dropout: float = 0):
         super().__init__()

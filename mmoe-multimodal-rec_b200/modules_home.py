@@ -79,6 +79,7 @@ class HOME_MMoE_Complete(_Native):
     """Hierarchical-expert two-task head (reference model_HoME.py:530-638)."""
 
     _lowp_exclude = ("fc.weight", "tower_good.4.weight", "tower_best.4.weight")
+    _fusable = True
 
     def __init__(self, num_input_experts: int = 6, expert_dim: int = 768, n_shared_experts: int = 4,
                  n_task_experts: int = 2, tower_hidden: int = 256):

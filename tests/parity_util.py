@@ -92,8 +92,10 @@ def run_cuda(case: C.Case, mode: str = "fp32", module=None, seed=None):
     torch.autograd.backward(list(outs), [c.to(o.device, o.dtype) for c, o in zip(cots, outs)])
     torch.cuda.synchronize()
     gin = [t.grad.detach().float().cpu() if f else None for t, f in zip(ins, meta)]
-    gp = OrderedDict((n, (p.grad.detach().float().cpu() if p.grad is not None else None))
-                     for n, p in mod.named_parameters() if not n.startswith("backbone") and not n.startswith("vit_model"))
+    # per-name gradients; modules in fused-parameter mode (MMOE_FLAT_PARAMS=1) expose them as slices of _flat_param.grad
+    named = mod.named_gradients() if hasattr(mod, "named_gradients") else [(n, p.grad) for n, p in mod.named_parameters()]
+    gp = OrderedDict((n, (g.detach().float().cpu() if g is not None else None))
+                     for n, g in named if not n.startswith("backbone") and not n.startswith("vit_model"))
     return [o.detach().float().cpu() for o in outs], gin, gp
 
 

@@ -31,13 +31,17 @@ def _batch(B, seed):
     }
 
 
-def _build(dev):
+def _build(dev, fused=False):
     import mmoe_multimodal_rec_b200 as pkg
     from parity_util import FakeBackbone
     M = pkg.modules
     torch.manual_seed(4321)
-    mods = {"img": M.ItemImageExpert(FakeBackbone(), pool_type="mean"), "cross": M.RobustTextCrossExpert(),
-            "concat_ui": M.EnhancedCrossFuse(), "concat_ti": M.EnhancedCrossFuse(), "head": M.TwoTaskMMoE()}
+    pkg.functional.set_flat_parameters(fused)       # fused-parameter mode: one nn.Parameter per module (modules._Native)
+    try:
+        mods = {"img": M.ItemImageExpert(FakeBackbone(), pool_type="mean"), "cross": M.RobustTextCrossExpert(),
+                "concat_ui": M.EnhancedCrossFuse(), "concat_ti": M.EnhancedCrossFuse(), "head": M.TwoTaskMMoE()}
+    finally:
+        pkg.functional.set_flat_parameters(False)
     for m in mods.values():
         m.to(dev).eval()
     return mods
@@ -61,7 +65,11 @@ def _step(mods, call, b, autocast_dtype):
 
 
 def _grads(mods):
-    return {f"{k}.{n}": p.grad.detach().clone() for k, m in mods.items() for n, p in m.named_parameters() if p.grad is not None}
+    out = {}
+    for k, m in mods.items():
+        named = m.named_gradients() if hasattr(m, "named_gradients") else [(n, p.grad) for n, p in m.named_parameters()]
+        out.update({f"{k}.{n}": g.detach().clone() for n, g in named if g is not None})
+    return out
 
 
 def _worker(rank, world, port, mode, q):
@@ -75,6 +83,8 @@ def _worker(rank, world, port, mode, q):
     Fn = pkg.functional
     dtype = {"fp32": None, "bf16": torch.bfloat16}[mode.split("/")[1]]
     how = mode.split("/")[0]
+    fused = how.endswith("flat")
+    how = how[:-4] if fused else how
     B = 16
     full = {k: v.to(dev) for k, v in _batch(B, 7).items()}
     shard = {k: v[rank * (B // world):(rank + 1) * (B // world)].contiguous() for k, v in full.items()}
@@ -86,6 +96,17 @@ def _worker(rank, world, port, mode, q):
     for m in mods.values():
         m.zero_grad(set_to_none=True)
     problems = []
+    if fused:
+        # the reference gradient above comes from the per-tensor modules; the exchange is tested on fused-parameter
+        # modules that received the same weights through load_state_dict (reference keys)
+        fmods = _build(dev, fused=True)
+        for k in mods:
+            fmods[k].load_state_dict(mods[k].state_dict())
+        n_par = {k: len(list(m.parameters())) for k, m in fmods.items()}
+        if any(n_par[k] != 1 for k in ("cross", "concat_ui", "concat_ti", "head")):
+            problems.append(f"fused modules expose {n_par} parameters")
+        mods = fmods
+        plain = {k: m for k, m in mods.items()}
 
     def compare(tag, scale=1.0, skip_prefix=()):
         got = _grads(mods)
@@ -144,7 +165,7 @@ def _worker(rank, world, port, mode, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["native/fp32", "native/bf16", "ddp/fp32", "ddp/bf16"])
+@pytest.mark.parametrize("mode", ["native/fp32", "native/bf16", "ddp/fp32", "ddp/bf16", "ddpflat/fp32", "ddpflat/bf16", "nativeflat/bf16"])
 def test_two_rank_gradients_equal_full_batch_gradient(mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")

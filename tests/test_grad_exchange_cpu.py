@@ -49,7 +49,7 @@ class _StubLib:
             return lambda: b"stub"
         if name in ("mmoe_head_fwd", "mmoe_home_fwd", "mmoe_cross_fwd", "mmoe_fuse_fwd", "mmoe_img_pool_fwd", "mmoe_cast_f32"):
             return lambda *a: 0
-        if name in ("mmoe_head_bwd", "mmoe_home_bwd", "mmoe_fuse_bwd"):
+        if name in ("mmoe_head_bwd", "mmoe_home_bwd", "mmoe_fuse_bwd", "mmoe_cross_bwd"):
             def bwd(call, *a):
                 self._fill(call, range(self._n_current))
                 return 0
@@ -94,6 +94,7 @@ def _worker(rank, world, port, q):
 
     torch.manual_seed(0)
     d = 64
+    Fn.set_flat_parameters(False)          # this file tests the per-tensor parameter mode (fused mode: test_flat_params_cpu.py)
     mods = {
         "cross": M.RobustTextCrossExpert(d=d, n_layer=2, n_head=8),
         "cross_home": H.RobustTextCrossExpert(d=d, n_layer=2, n_head=8),
