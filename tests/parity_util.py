@@ -37,8 +37,16 @@ def case_kwargs(case: C.Case):
     return dict(case.ctor)
 
 
-def build_module(case: C.Case, device="cuda"):
+def build_module(case: C.Case, device="cuda", fused=None):
+    """fused: None = the package default (fused-parameter mode unless MMOE_FLAT_PARAMS=0), True / False = explicit."""
     import mmoe_multimodal_rec_b200 as pkg
+    if fused is not None:
+        was = pkg.functional.FLAT_PARAMS
+        pkg.functional.set_flat_parameters(fused)
+        try:
+            return build_module(case, device)
+        finally:
+            pkg.functional.set_flat_parameters(was)
     M, H = pkg.modules, pkg.modules_home
     k = case.kind
     if k == "head":

@@ -153,6 +153,29 @@ def test_scoring_order_matches_in_fp32():
         assert abs(auc(a) - auc(r)) < 1e-6
 
 
+@pytest.mark.parametrize("name", ["head_b16", "home_head_b8", "fuse_b8", "fuse_home_b8", "cross_b3", "cross_home_b3"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_parameter_modes_agree(name, mode):
+    """Per-tensor parameters (staged cross-expert backward, ~60 gradients handed to autograd) and the fused parameter
+    (one backward node, the flat buffer is the gradient) run the same kernels: same outputs, same per-name gradients."""
+    case = C.CASES_BY_NAME[name]
+    per_tensor = PU.build_module(case, fused=False)
+    fused = PU.build_module(case, fused=True)
+    assert len(list(fused.parameters())) == 1 + len(set(case.shapes()) - set(case.used_param_keys()))
+    assert list(fused.state_dict().keys()) == list(per_tensor.state_dict().keys())
+    oa, gia, gpa = PU.run_cuda(case, mode, module=per_tensor)
+    ob, gib, gpb = PU.run_cuda(case, mode, module=fused)
+    for a, b in zip(oa, ob):
+        assert torch.equal(a, b)
+    for a, b in zip(gia, gib):
+        assert (a is None) == (b is None) and (a is None or PU.nerr(b, a) <= 1e-6)
+    assert list(gpa.keys()) == list(gpb.keys())
+    for k in gpa:
+        assert (gpa[k] is None) == (gpb[k] is None), k
+        if gpa[k] is not None:
+            assert PU.nerr(gpb[k], gpa[k]) <= 1e-5, k
+
+
 def test_unused_home_parameters_keep_grad_none():
     for name in ("cross_home_b3", "fuse_home_b8"):
         case = C.CASES_BY_NAME[name]
