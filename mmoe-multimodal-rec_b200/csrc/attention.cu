@@ -194,6 +194,7 @@ constexpr int SMALL_S = 4, SMALL_C = 4;   // S <= 4, head_dim <= 128
 template <typename T>
 __global__ void __launch_bounds__(256) attn_small_kernel(const AttnDev a, int bwd) {
   __shared__ float red[8][3 * 128];
+  pdl_entry();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x * 8 + warp, h = blockIdx.y;
   const int hd = a.hd, Sq = a.Sq, Sk = a.Sk;
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const AttnDev a, int bw
 template <typename T>
 static int launch_small(const AttnDev& d, int bwd, cudaStream_t s) {
   dim3 grid((unsigned)((d.B + 7) / 8), (unsigned)d.H);
-  attn_small_kernel<T><<<grid, 256, 0, s>>>(d, bwd);
+  MMOE_CUDA(launch_pdl(attn_small_kernel<T>, grid, 256, 0, s, d, bwd));
   MMOE_LAUNCH_OK("attn_small_kernel");
   return 0;
 }

@@ -154,6 +154,7 @@ template <typename T, int HD>
 __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcDev a) {
   constexpr int PITCH = HD + 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_entry();
   T* Qs = reinterpret_cast<T*>(smem_raw);
   T* Ks = Qs + 64 * PITCH;
   T* Vs = Ks + 64 * PITCH;
@@ -260,6 +261,7 @@ template <typename T, int HD>
 __global__ void __launch_bounds__(128) attn_tc_bwd_kernel(const AttnTcDev a) {
   constexpr int PITCH = HD + 8, PP = 72;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_entry();
   T* Qs = reinterpret_cast<T*>(smem_raw);
   T* Ks = Qs + 64 * PITCH;
   T* Vs = Ks + 64 * PITCH;
@@ -488,13 +490,13 @@ static int launch_tc(const AttnArgs& a, bool bwd, cudaStream_t s) {
     const size_t smem = (size_t)3 * 64 * (HD + 8) * sizeof(T);
     static bool cfg = false;
     if (!cfg) { MMOE_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<T, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
-    attn_tc_fwd_kernel<T, HD><<<a.B * a.H, threads, smem, s>>>(d);
+    MMOE_CUDA(launch_pdl(attn_tc_fwd_kernel<T, HD>, a.B * a.H, threads, smem, s, d));
     MMOE_LAUNCH_OK("attn_tc_fwd_kernel");
   } else {
     const size_t smem = (size_t)4 * 64 * (HD + 8) * sizeof(T) + (size_t)64 * 72 * sizeof(T) + 4 * 3 * HD * sizeof(float);
     static bool cfg = false;
     if (!cfg) { MMOE_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<T, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
-    attn_tc_bwd_kernel<T, HD><<<a.B * a.H, threads, smem, s>>>(d);
+    MMOE_CUDA(launch_pdl(attn_tc_bwd_kernel<T, HD>, a.B * a.H, threads, smem, s, d));
     MMOE_LAUNCH_OK("attn_tc_bwd_kernel");
   }
   return 0;

@@ -50,6 +50,36 @@ cudaError_t last_launch_status(const char* what);
     if (_r != 0) return _r;   \
   } while (0)
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// A kernel launched through launch_pdl() may be scheduled while the kernel before it in the stream is still running: its
+// CTAs start as SM resources come free, run their on-chip prologue (barrier init, TMEM allocation, descriptor prefetch) and
+// block in pdl_wait() until the WHOLE preceding grid has completed and its memory is visible.  Rule for every such kernel:
+// nothing before pdl_wait() reads or writes global memory.  pdl_launch_dependents() — issued right AFTER the wait, so that
+// at most one dependent grid is ever pre-launched — lets the next PDL kernel do the same behind this one.  The step has
+// ~140 back-to-back launches on its critical stream with 2-3 us between them (profiles/r02_exchange_trace.md).  Opt-in
+// (MMOE_PDL=1 sets the launch attribute; without it the two instructions are no-ops): see pdl_enabled() for the measurement.
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() { pdl_wait(); pdl_launch_dependents(); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---------------------------------------------------------------- dtype helpers
 template <typename T> struct DT;
 template <> struct DT<float> { static constexpr int id = MMOE_F32; };

@@ -589,6 +589,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above (barrier init, TMEM allocation, cluster handshakes) touched only on-chip
+  // state and may run while the previous kernel of the stream drains; global memory is first touched below
+  pdl_entry();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -1202,14 +1205,16 @@ static int launch_tc(const mmoe_gemm_problem* pr_in, int n, int dtype, cudaStrea
     cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = TC_SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     MMOE_CUDA(cudaLaunchKernelEx(&cfg, kernels[3][rich ? 1 : 0], P));
   } else {
     const int grid = tiles < avail ? tiles : avail;
-    kernels[bn == 64 ? 0 : (bn == 128 ? 1 : 2)][rich ? 1 : 0]<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(P);
+    MMOE_CUDA(launch_pdl(kernels[bn == 64 ? 0 : (bn == 128 ? 1 : 2)][rich ? 1 : 0], grid, TC_THREADS, TC_SMEM_BYTES, stream, P));
   }
   MMOE_LAUNCH_OK("gemm_tc_kernel");
   t_last_bn = bn; t_last_ctas = ctas;
