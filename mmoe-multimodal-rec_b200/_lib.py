@@ -176,7 +176,4 @@ def check(rc: int, what: str = ""):
 
 
 def ptr_array(ptrs):
-    arr = (C.c_void_p * len(ptrs))()
-    for i, p in enumerate(ptrs):
-        arr[i] = p
-    return arr
+    return (C.c_void_p * len(ptrs))(*ptrs)

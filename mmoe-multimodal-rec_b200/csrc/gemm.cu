@@ -1005,6 +1005,23 @@ static int make_tmap(CUtensorMap* map, const void* ptr, int dtype, int64_t rows,
   MMOE_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   MMOE_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "GEMM operand pointer must be 16-byte aligned");
   MMOE_CHECK((ld * 2) % 16 == 0, "GEMM operand leading dimension must be a multiple of 8 elements (got %lld)", (long long)ld);
+  // The descriptor is a pure function of (pointer, dtype, extents, stride, box): a step encodes ~300 of them, nearly all
+  // with the arguments of the step before (torch's caching allocator hands the same blocks back), so they are kept in a
+  // small per-thread direct-mapped table instead of being re-encoded by the driver.
+  struct Key { const void* ptr; int64_t rows, cols, ld; int dtype, box_rows; };
+  struct Slot { Key k; CUtensorMap m; bool used; };
+  constexpr int kSlots = 4096;
+  thread_local Slot* table = nullptr;
+  if (table == nullptr) table = new Slot[kSlots]();
+  uint64_t h = reinterpret_cast<uintptr_t>(ptr) >> 4;
+  h = (h ^ (uint64_t)rows * 0x9E3779B97F4A7C15ull ^ (uint64_t)cols * 0xC2B2AE3D27D4EB4Full ^ (uint64_t)ld * 0x165667B19E3779F9ull ^
+       (uint64_t)(dtype * 131 + box_rows)) * 0xD6E8FEB86659FD93ull;
+  Slot& sl = table[(h >> 32) & (kSlots - 1)];
+  if (sl.used && sl.k.ptr == ptr && sl.k.rows == rows && sl.k.cols == cols && sl.k.ld == ld && sl.k.dtype == dtype &&
+      sl.k.box_rows == box_rows) {
+    *map = sl.m;
+    return 0;
+  }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
@@ -1014,6 +1031,9 @@ static int make_tmap(CUtensorMap* map, const void* ptr, int dtype, int64_t rows,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MMOE_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r,
              (long long)rows, (long long)cols, (long long)ld);
+  sl.k = Key{ptr, rows, cols, ld, dtype, box_rows};
+  sl.m = *map;
+  sl.used = true;
   return 0;
 }
 

@@ -81,9 +81,18 @@ class ParamPack:
         self.names = list(names)
         self.lowp = set(lowp)
         self._cache = {}
+        self._stable = {}
 
-    def tensors(self, params: Sequence[torch.Tensor], dtype: int) -> List[torch.Tensor]:
-        out = []
+    def tensors(self, params: Sequence[torch.Tensor], dtype: int, flat: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+        """flat: the fused parameter that owns the storage of `params` (fused-parameter modules).  While its version
+        counter and address are unchanged, the tensors handed to the library are the ones of the previous call: the whole
+        list — with its ctypes pointer array and gradient-buffer plan — is reused instead of being rebuilt per call."""
+        if flat is not None:
+            key = (dtype, flat._version, flat.data_ptr(), len(params))
+            hit = self._stable.get(dtype)
+            if hit is not None and hit.key == key:
+                return hit
+        out = _Stable() if flat is not None else []
         L = lib()
         for name, p in zip(self.names, params):
             _require_cuda(p)
@@ -95,15 +104,26 @@ class ParamPack:
             if dtype == F32 or name not in self.lowp:
                 out.append(pd)
                 continue
-            key = (name, dtype)
-            ent = self._cache.get(key)
+            key_c = (name, dtype)
+            ent = self._cache.get(key_c)
             if ent is None or ent[0] != p._version or ent[1] != pd.data_ptr() or ent[2].device != pd.device:
                 q = torch.empty(pd.shape, dtype=_MMOE2TORCH[dtype], device=pd.device)
                 check(L.mmoe_cast_f32(pd.data_ptr(), q.data_ptr(), pd.numel(), dtype, _stream()), "cast")
                 ent = (p._version, pd.data_ptr(), q)
-                self._cache[key] = ent
+                self._cache[key_c] = ent
             out.append(ent[2])
+        if flat is not None:
+            out.key = key
+            out.arr = ptr_array([t.data_ptr() for t in out])
+            out.plans = {}
+            self._stable[dtype] = out
         return out
+
+
+class _Stable(list):
+    """Parameter tensor list of a fused-parameter module that stays valid until the parameter changes; carries the
+    ctypes pointer array (`arr`) and the gradient-buffer plans (`plans`) derived from it."""
+    __slots__ = ("key", "arr", "plans")
 
 
 _LAYOUTS = {}
@@ -136,6 +156,15 @@ def _alloc_grads(params: Sequence[torch.Tensor], used: Sequence[bool], want_view
     (views, pointer list, flat buffer).  One as_strided per parameter: the view creation is host time on the critical
     path of every backward (≈300 parameters per step).  want_views=False (fused-parameter modules, whose single
     parameter takes the flat buffer itself as its gradient): views is None."""
+    if not want_views and isinstance(params, _Stable):
+        plan = params.plans.get("grads")
+        if plan is None or plan[2] != list(used):
+            total, entries = _grad_layout(params, used)
+            plan = (total, [None if e is None else 4 * e[0] for e in entries], list(used))
+            params.plans["grads"] = plan
+        flat = torch.zeros(plan[0], dtype=torch.float32, device=params[0].device)
+        base = flat.data_ptr()
+        return None, [None if o is None else base + o for o in plan[1]], flat
     total, entries = _grad_layout(params, used)
     flat = torch.zeros(total, dtype=torch.float32, device=params[0].device)
     base = flat.data_ptr()
@@ -383,7 +412,7 @@ def _call(dtype, B, training, home, drop_p, seed, ptensors, grad_ptrs, saved, wo
     c = Call()
     c.dtype, c.B, c.training, c.home = dtype, B, int(training), int(home)
     c.drop_p, c.seed = float(drop_p), int(seed)
-    pa = ptr_array([t.data_ptr() for t in ptensors])
+    pa = ptensors.arr if isinstance(ptensors, _Stable) else ptr_array([t.data_ptr() for t in ptensors])
     c.params = C.cast(pa, C.POINTER(C.c_void_p))
     c._keep = [pa, ptensors]
     if grad_ptrs is not None:
@@ -413,7 +442,7 @@ class HeadFn(torch.autograd.Function):
         ev = _f32c(expert_vecs)
         B, dev = ev.shape[0], ev.device
         params, ctx.flat_p = _split_fused(pack, params)
-        pt = pack.tensors(params, dtype)
+        pt = pack.tensors(params, dtype, ctx.flat_p)
         fwd, bwd, sb, wb = ((L.mmoe_head_fwd, L.mmoe_head_bwd, L.mmoe_head_saved_bytes, L.mmoe_head_workspace_bytes) if kind == "mmoe"
                             else (L.mmoe_home_fwd, L.mmoe_home_bwd, L.mmoe_home_saved_bytes, L.mmoe_home_workspace_bytes))
         saved = _bytes(sb(C.byref(cfg), B, dtype), dev)
@@ -469,7 +498,7 @@ class CrossFn(torch.autograd.Function):
         im = item_mask.detach().to(torch.bool).contiguous().view(torch.uint8)
         B, dev = u.shape[0], u.device
         params, ctx.flat_p = _split_fused(pack, params)
-        pt = pack.tensors(params, dtype)
+        pt = pack.tensors(params, dtype, ctx.flat_p)
         saved = _bytes(L.mmoe_cross_saved_bytes(C.byref(cfg), B, dtype), dev)
         out = torch.empty((B, cfg.d), dtype=torch.float32, device=dev)
         seed = _new_seed(training, drop_p)
@@ -675,7 +704,7 @@ class FuseFn(torch.autograd.Function):
         v, t = _f32c(v_cls), _f32c(t_cls)
         B, dev = v.shape[0], v.device
         params, ctx.flat_p = _split_fused(pack, params)
-        pt = pack.tensors(params, dtype)
+        pt = pack.tensors(params, dtype, ctx.flat_p)
         saved = _bytes(L.mmoe_fuse_saved_bytes(C.byref(cfg), B, dtype), dev)
         out = torch.empty((B, cfg.d), dtype=torch.float32, device=dev)
         seed = _new_seed(training, drop_p)
