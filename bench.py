@@ -425,8 +425,24 @@ def home_ddp_measurement(dev, local_rank, world, steps):
     t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    return {"B_per_gpu": B, "ms_per_step": ms, "samples_per_s": B * world / (ms * 1e-3), "steps": steps,
-            "wrapping": "13 DistributedDataParallel(find_unused_parameters=True) wrappers, script-side BN wrappers / InfoNCE in torch"}
+    out = {"B_per_gpu": B, "ms_per_step": ms, "samples_per_s": B * world / (ms * 1e-3), "steps": steps,
+           "wrapping": "13 DistributedDataParallel(find_unused_parameters=True) wrappers, script-side BN wrappers / InfoNCE in torch"}
+    trace = os.environ.get("BENCH_HOME_TRACE")
+    if trace:                                     # device timeline of 3 more steps (tools/trace_exchange.py's reduction)
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                step()
+            dist.barrier(); torch.cuda.synchronize()
+        if dist.get_rank() == 0:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import trace_exchange
+            prof.export_chrome_trace(trace)
+            r = trace_exchange.analyse(trace, 3)
+            fams = sorted(r.pop("families").items(), key=lambda kv: -kv[1]["ms_per_step"])[:12]
+            r.pop("streams", None)
+            out["timeline"] = r | {"top_kernel_families": {k: v for k, v in fams}}
+    return out
 
 
 def small_batch_measurement(dev, step_factory, B_small, ms_per_sample_ref):
