@@ -189,6 +189,15 @@ class _Native(nn.Module, metaclass=_NativeMeta):
         return [(n, (None if g is None else g.as_strided(fused[n][1], fused[n][2], fused[n][0])) if n in fused else rest[n].grad)
                 for n in self.__dict__["_mmoe_names"]]
 
+    _CACHE_KEYS = ("_mmoe_params", "_mmoe_pack", "_mmoe_flat_ptr", "_mmoe_flat_dev")
+
+    def __getstate__(self):
+        # torch.save(module) / pickle: the per-call caches hold ctypes pointer arrays and device addresses of this process
+        st = self.__dict__.copy()
+        for k in self._CACHE_KEYS:
+            st.pop(k, None)
+        return st
+
     def __deepcopy__(self, memo):
         # the default deep copy keeps the aliasing of tensors that share a storage, but the per-name views live in the
         # sub-modules' __dict__ next to cached pointers: rebuild them on the copy rather than rely on that
@@ -196,9 +205,8 @@ class _Native(nn.Module, metaclass=_NativeMeta):
         cls = self.__class__
         new = cls.__new__(cls)
         memo[id(self)] = new
-        skip = ("_mmoe_params", "_mmoe_pack", "_mmoe_flat_ptr", "_mmoe_flat_dev")
         for k, v in self.__dict__.items():
-            if k not in skip:
+            if k not in self._CACHE_KEYS:
                 new.__dict__[k] = copy.deepcopy(v, memo)
         if "_mmoe_fused" in new.__dict__:
             new._rebuild_views()

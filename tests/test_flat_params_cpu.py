@@ -105,6 +105,17 @@ def test_views_follow_the_parameter():
     assert m3.layers[0].linear1.weight.untyped_storage().data_ptr() == m3._flat_param.untyped_storage().data_ptr()
     m.requires_grad_(False)
     assert not m._flat_param.requires_grad
+    # whole-module pickling (torch.save(module)): caches stay behind, views are rebuilt on first use
+    import io
+    m._pack().tensors  # noqa: B018  (make sure a pack exists)
+    buf = io.BytesIO()
+    torch.save(m2, buf)
+    buf.seek(0)
+    m4 = torch.load(buf, weights_only=False)
+    m4._params()
+    assert torch.equal(m4.state_dict()["layers.0.linear1.weight"], m2.state_dict()["layers.0.linear1.weight"])
+    m4._flat_param.data.mul_(2.0)
+    assert torch.equal(m4.layers[0].linear1.weight, 2.0 * m2.layers[0].linear1.weight)
 
 
 # ----------------------------------------------------------------------------------------------
