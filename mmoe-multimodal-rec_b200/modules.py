@@ -115,6 +115,13 @@ class _Native(nn.Module, metaclass=_NativeMeta):
             self.__dict__["_mmoe_params"] = ps
         return ps
 
+    def invalidate_weight_cache(self):
+        """Forget the cached 16-bit copies of the GEMM weights.  They are refreshed automatically whenever a parameter's
+        version counter moves (optimizer steps, load_state_dict, any in-place op on the parameter); writes that bypass the
+        counter — ``param.data.mul_(...)``-style updates — need this call."""
+        self.__dict__.pop("_mmoe_params", None)
+        self.__dict__.pop("_mmoe_pack", None)
+
     def _apply(self, fn, *args, **kwargs):
         self.__dict__.pop("_mmoe_params", None)
         self.__dict__.pop("_mmoe_pack", None)
