@@ -103,6 +103,40 @@ def test_16bit_forward_matches_fp64_oracle_without_any_injection():
             assert PU.nerr(a, b) <= PU.TOL["bf16"], name
 
 
+@pytest.mark.parametrize("name", ["cross_b3", "fuse_b8", "head_b16"])
+def test_bf16_is_as_close_to_fp64_as_eager_autocast(name):
+    """besides "within 2e-2 of fp64", say how the kernels compare with what the reference itself
+    computes under the same autocast — the stock torch.nn modules (oracle/eager_ref.py: cuBLASLt / SDPA / native
+    LayerNorm) on this GPU, same weights and inputs, eval mode.  Outputs and input gradients of both are measured against
+    the un-injected fp64 oracle; the native path may be at most 2.5x further from fp64 than eager (with a floor of a
+    quarter of the 16-bit tolerance, below which both are at rounding noise)."""
+    from oracle import eager_ref as E
+    case = C.CASES_BY_NAME[name]
+    make, fwd = {"cross": (E.make_cross_expert, E.cross_expert), "fuse": (E.make_cross_fuse, E.cross_fuse),
+                 "head": (E.make_mmoe_head, lambda m, x: E.two_task_mmoe(m, x))}[case.kind]
+    eager = make().cuda().eval()
+    eager.load_state_dict(case.state_dict(), strict=True)
+    meta = case.inputs_meta()
+    ins = [t.cuda().clone().requires_grad_(True) if f else t.cuda() for t, f in zip(case.inputs(), meta)]
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = fwd(eager, *ins)
+    outs = tuple(out) if isinstance(out, (tuple, list)) else (out,)
+    cots = case.cotangents([o.detach().cpu() for o in outs])
+    torch.autograd.backward(list(outs), [c.to(o.device, o.dtype) for c, o in zip(cots, outs)])
+    e_out = [o.detach().float().cpu() for o in outs]
+    e_gin = [t.grad.detach().float().cpu() if f else None for t, f in zip(ins, meta)]
+    o_out, o_gin, _ = C.run_oracle(case, torch.float64)
+    c_out, c_gin, _ = PU.run_cuda(case, "bf16")
+    floor = 0.25 * PU.TOL["bf16"]
+    report = {}
+    for tag, ours, theirs, ref in ([(f"out{j}", a, b, r) for j, (a, b, r) in enumerate(zip(c_out, e_out, o_out))] +
+                                   [(f"grad_in{j}", a, b, r) for j, (a, b, r) in enumerate(zip(c_gin, e_gin, o_gin)) if r is not None]):
+        report[tag] = (PU.nerr(ours, ref), PU.nerr(theirs, ref))
+    print(f"[eager-vs-native] {name}: " + ", ".join(f"{k} native {v[0]:.2e} / eager {v[1]:.2e}" for k, v in report.items()))
+    bad = {k: v for k, v in report.items() if not v[0] <= max(2.5 * v[1], floor)}
+    assert not bad, f"{name}: (native err, eager err) vs fp64: {report}"
+
+
 def test_gate_argmax_identical_in_fp32():
     """north_star: gate argmax bit-identical on the fp32 path (wherever the fp64 top-2 margin exceeds 1e-5,
     i.e. beyond what any fp32 summation order can resolve — SURVEY.md §7.2)."""
